@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — particle-updates/s of the WCSPH step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one leapfrog step (kick, drift, cell build, density+pressure, accelerations,
+kick: pi_sph_fluid.c:612-641) over every fluid particle of the workload.
+
+N = 1 workload: BASELINE.json configs[1] — the reference's drop scene scaled to R = 0.002423
+(262,204 fluid + 4,954 boundary particles), synthetic (the reference's own lattice).
+
+Keys of the JSON line (see the round prompt for the contract):
+  value         whole-job fluid-particle-updates/s, state resident in HBM, CUDA events on the
+                library's stream around each step, L2 flushed between steps (untimed)
+  e2e           same metric through the C ABI with HOST buffers: sphb_upload (pinned host ->
+                HBM) + K x (sphb_step with that step's gravity + sphb_get_stats read-back) +
+                sphb_download, all inside the timed region
+  roofline      dominant kernel (k_force): algorithmic bytes / launch over its mean CUDA-event
+                duration vs MEASURED_PEAKS.json hbm_gbs; `fp32` gives the binding roof
+  cpu_baseline  the reference's own compiled code (oracle/_ref, OpenMP) on this host, bounded sample
+  --impl reference   the reference arm: times oracle/_ref only (rank 0), same workload/metric
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "fluid-particle-updates/sec"
+UNIT = "particle-updates/s"
+G = (0.0, -9.81)
+
+# algorithmic HBM bytes / particle / launch (DESIGN.md "Kernels")
+ALGO_BYTES = {"advect_bin": 44.0, "reorder": 40.0, "density": 16.0, "force": 40.0}
+# algorithmic flops / particle: 6*C + 13*P (density), 6*C + 44*P (force); C, P measured by the run
+
+
+def workload_spec(name: str):
+    """-> dict(name, R, scene, args)"""
+    if name == "drop256k":
+        return dict(name="drop_R0.002423_262204_fluid_4954_boundary (BASELINE configs[1])", R=0.002423, scene="drop", ref_tag="0.002423")
+    if name == "drop61k":
+        return dict(name="drop_R0.005_61519_fluid", R=0.005, scene="drop", ref_tag="0.005")
+    if name == "drop4k":
+        return dict(name="drop_R0.02_3848_fluid", R=0.02, scene="drop", ref_tag="0.02")
+    if name == "drop269":
+        return dict(name="drop_R0.075_269_fluid (BASELINE configs[0])", R=0.075, scene="drop", ref_tag=None)
+    if name == "dam4m":
+        return dict(name="dam_break_R0.0005_4M (BASELINE configs[2])", R=0.0005, scene="dam", block=(2.0, 0.5), ref_tag=None)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def read_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(pkg, spec, deterministic=True, device=0):
+    prm = pkg.default_params(spec["R"], deterministic=deterministic, device=device)
+    if spec["scene"] == "drop":
+        fluid = pkg.scene_drop(prm)
+    else:
+        x1, y1 = spec["block"]
+        fluid = pkg.scene_block(prm, spec["R"], x1, spec["R"], y1)
+    boundary = pkg.scene_boundary(prm)
+    return prm, fluid, boundary
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+def run_reference(spec, steps: int, warmup: int, budget_s: float = 90.0):
+    """Times the reference's own compiled operators (oracle/_ref, shipped -Ofast flags, OpenMP
+    over all host cores) on the workload.  Returns dict or None if unavailable."""
+    from oracle import pyoracle
+    tag = spec["ref_tag"]
+    R = spec["R"]
+    if spec["scene"] != "drop":
+        return None
+    kind = "reference"
+    try:
+        if not pyoracle.reference_available(tag, "fast"):
+            raise FileNotFoundError
+        ref = pyoracle.Reference(R=tag, flavour="fast")
+    except (FileNotFoundError, OSError):
+        ref = None
+    o = pyoracle.Oracle(R=R, variant="fast")
+    fluid, boundary = o.scene_drop(), o.scene_boundary()
+    cores = os.cpu_count() or 1
+    if ref is not None:
+        cores = min(cores, ref.max_threads)
+        cb = ref.init_boundary(boundary); cf = ref.ctx(len(fluid))
+        du, dv = ref.compute_accel(fluid, boundary, cf, cb, *G)
+        run = lambda n: ref.step(fluid, boundary, cf, cb, du, dv, n, *G, threads=cores)
+    else:
+        kind = "port"
+        gb = o.init_boundary(boundary); gf = o.grid(len(fluid))
+        du, dv = o.compute_accel(fluid, boundary, gf, gb, *G)
+        cores = o.threads
+
+        def run(n):
+            t0 = time.perf_counter(); o.step(fluid, boundary, gf, gb, du, dv, n, *G); return time.perf_counter() - t0
+    t_probe = run(max(1, min(warmup, 3)))
+    per_step = t_probe / max(1, min(warmup, 3))
+    n_run = int(max(1, min(steps, budget_s / max(per_step, 1e-9))))
+    t = run(n_run)
+    return {"value": len(fluid) * n_run / t, "unit": UNIT, "cores": int(cores), "kind": kind,
+            "sample": f"{n_run} of {steps} steps of the full {len(fluid)}-particle scene, {t:.2f} s",
+            "ms_per_step": 1e3 * t / n_run, "n_fluid": int(len(fluid)), "steps_run": n_run}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+def run_gpu(args, spec, rank, world):
+    import torch
+    import pi_sph_fluid_b200 as pkg
+
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    prm, fluid, boundary = build_scene(pkg, spec, deterministic=not args.nondeterministic, device=dev)
+    n = len(fluid)
+    K, W = args.steps, max(args.warmup, 3)
+
+    sim = pkg.Simulation(prm)
+    stream = torch.cuda.ExternalStream(sim.stream, device=dev)
+    sim.upload(fluid, boundary)
+    sim.init_boundary()
+    sim.compute_accel(*G)
+    sim.step(W, *G)
+    sim.synchronize()
+    cand, acc = sim.pair_stats()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: K steps, per-step events on the library's stream, L2 flushed between steps
+    clocks = ClockSampler(dev)
+    clocks.start()
+    launches0 = sim.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        sim.flush_l2()
+        a.record(stream)
+        sim.step(1, *G)
+        b.record(stream)
+    sim.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    gpu_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = sim.launch_count - launches0
+    clk = clocks.stop()
+    if world > 1:
+        tmax = torch.tensor([gpu_ms], device=f"cuda:{dev}")
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        gpu_ms = float(tmax.item())
+    total_particles = n * world
+    value = total_particles * K / (gpu_ms * 1e-3)
+
+    # ---- warm-L2 variant (steady state of a resident simulation), for reference in config
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record(stream); sim.step(K, *G); b.record(stream)
+    sim.synchronize()
+    warm_ms = a.elapsed_time(b)
+
+    # ---- per-kernel CUDA-event times (separate pass: events between kernels perturb the step)
+    sim.profile(1)
+    sim.profile_read(reset=True)
+    for _ in range(K):
+        sim.flush_l2()
+        sim.step(1, *G)
+    prof = sim.profile_read(reset=True)
+    sim.profile(0)
+    hbm_peak, sm_max_mhz, peak_src = read_peaks()
+    kern = {}
+    for name, d in prof.items():
+        if d["launches"] == 0:
+            continue
+        ms = d["ms"] / d["launches"]
+        kern[name] = {"ms": round(ms, 5), "launches_per_step": d["launches"] / K}
+        if name in ALGO_BYTES:
+            kern[name]["algo_GBps"] = round(ALGO_BYTES[name] * n / (ms * 1e-3) / 1e9, 2)
+    force_ms = prof["force"]["ms"] / max(1, prof["force"]["launches"])
+    dens_ms = prof["density"]["ms"] / max(1, prof["density"]["launches"])
+    achieved = ALGO_BYTES["force"] * n / (force_ms * 1e-3) / 1e9
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    force_flops = (6 * cand + 44 * acc) * n
+    dens_flops = (6 * cand + 13 * acc) * n
+    roofline = {
+        "kernel": "k_force", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
+        "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_particle": ALGO_BYTES["force"],
+        "note": "k_force and k_density are FP32-issue-bound, not HBM-bound (SURVEY.md §8d); see fp32",
+        "fp32": {"force_TFLOPs": round(force_flops / (force_ms * 1e-3) / 1e12, 3),
+                 "density_TFLOPs": round(dens_flops / (dens_ms * 1e-3) / 1e12, 3),
+                 "peak_TFLOPs": round(fp32_peak, 1), "peak_def": f"{sm_count} SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz",
+                 "force_frac": round(force_flops / (force_ms * 1e-3) / 1e12 / fp32_peak, 4),
+                 "density_frac": round(dens_flops / (dens_ms * 1e-3) / 1e12 / fp32_peak, 4),
+                 "pairs_per_particle": {"candidates": round(cand, 2), "accepted": round(acc, 2)}},
+        "kernels": kern,
+    }
+
+    # ---- e2e: host buffers -> C ABI -> host buffers, copies inside the timed region
+    fl_pin = torch.empty(n * 7, dtype=torch.float32).pin_memory()
+    bd_pin = torch.empty(len(boundary) * 7, dtype=torch.float32).pin_memory()
+    fl_host = fl_pin.numpy().view(pkg.PARTICLE); bd_host = bd_pin.numpy().view(pkg.PARTICLE)
+    fl_host[:] = fluid; bd_host[:] = boundary
+    out_pin = torch.empty(n * 7, dtype=torch.float32).pin_memory()
+    du_pin = torch.empty(n, dtype=torch.float32).pin_memory(); dv_pin = torch.empty(n, dtype=torch.float32).pin_memory()
+    out_host = out_pin.numpy().view(pkg.PARTICLE)
+    trace = np.tile(np.asarray([G], np.float32), (K, 1))
+    sim2 = pkg.Simulation(prm)
+    sim2.upload(fl_host, bd_host); sim2.init_boundary(); sim2.compute_accel(*G); sim2.step(W, *G); sim2.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    sim2.upload(fl_host, bd_host)                      # H2D: 28 B x (n_fluid + n_boundary)
+    sim2.init_boundary()
+    sim2.compute_accel(*G)
+    last = None
+    for s in range(K):
+        sim2.step_trace(trace[s:s + 1])                # that step's gravity sample (8 B)
+        last = sim2.stats()                            # D2H read-back of the step's statistics (:656-675)
+    sim2.download_into(out_host, du_pin.numpy(), dv_pin.numpy())     # D2H: 36 B x n_fluid
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=f"cuda:{dev}")
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    h2d = (28 * (n + len(boundary))) / K + 8
+    d2h = (36 * n) / K + 64 + 24
+    e2e = {"value": total_particles * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": round(h2d, 1),
+           "d2h_bytes_per_step": round(d2h, 1), "ms_per_step": round(1e3 * e2e_s / K, 5),
+           "path": "sphb_upload + K x (sphb_step_trace(1) + sphb_get_stats) + sphb_download, pinned host buffers",
+           "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
+    sim2.close()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (the reference's own lattice drop scene, pi_sph_fluid.c:484-540)",
+        "config": {"workload": spec["name"], "n_fluid": n, "n_boundary": int(len(boundary)), "R": spec["R"],
+                   "deterministic_order": not args.nondeterministic,
+                   "l2": "flushed between timed steps (256 MiB write on the same stream, untimed)",
+                   "warm_l2_value": total_particles * K / (warm_ms * 1e-3),
+                   "timing": "CUDA events on the library stream around each step; max over ranks",
+                   "wall_s_timed_region": round(t_wall, 4),
+                   "build": pkg.lib().sphb_build_info().decode()},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    sim.close()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--nondeterministic", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    spec = workload_spec(args.workload or "drop256k")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_reference(spec, args.steps, max(args.warmup, 3))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "no reference build for this workload"}))
+            return 0
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic (the reference's own lattice drop scene)",
+                "config": {"workload": spec["name"], "n_fluid": r["n_fluid"], "R": spec["R"],
+                           "threads": r["cores"], "flags": "-Ofast -march=x86-64-v3|v4 -fopenmp (Makefile:2,4; -march pinned for portability)"},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    if world > 1:
+        torch.distributed.init_process_group("nccl")
+    line = run_gpu(args, spec, rank, world)
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            r = run_reference(spec, 2000, 3, budget_s=15.0)
+            line["cpu_baseline"] = ({k: r[k] for k in ("value", "unit", "cores", "kind", "sample")} if r else None)
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,195 @@
+/* sph_b200.h — C ABI of libsphb200.so: the WCSPH per-timestep hot path of
+ * colonelwatch/pi-sph-fluid (pi_sph_fluid.c) on NVIDIA B200 (sm_100a).
+ *
+ * Plain C: opaque handle, plain pointers and sizes, int return codes (0 = ok, negative =
+ * SPHB_E_*), no exceptions, no hidden host threads, one CUDA stream per handle.  There is
+ * NO CPU fallback: every compute entry point returns SPHB_E_CUDA when no sm_100 device is
+ * usable.
+ *
+ * Two tiers:
+ *   1. resident tier  sphb_*      state lives in HBM between calls; what a host loop uses.
+ *   2. compat tier    the seven reference-named operators with the reference's exact
+ *                     signatures (upload -> kernels -> download per call), so the
+ *                     reference's main() links against this library unchanged.
+ *
+ * Each entry point cites the reference lines (pi_sph_fluid.c:NNN) it replaces.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)
+
+#define SPHB_VERSION 1
+
+enum {
+    SPHB_OK = 0,
+    SPHB_E_ARG = -1,      /* bad argument / call order                      */
+    SPHB_E_CUDA = -2,     /* CUDA runtime error or no usable sm_100 device  */
+    SPHB_E_NOMEM = -3,
+    SPHB_E_STATE = -4,    /* e.g. step before upload                        */
+    SPHB_E_COMM = -5      /* multi-GPU transport error                      */
+};
+
+/* Host-side particle record == `struct particle`, pi_sph_fluid.c:26-31 (7 x f32, 28 B). */
+typedef struct sphb_particle {
+    float x, y, u, v;
+    float m;
+    float rho;
+    float p;
+} sphb_particle;
+
+/* The reference's compile-time constants (pi_sph_fluid.c:10-21) as runtime fields, plus
+ * the grid geometry its main() passes to alloc_neighbors_context (:595-597). */
+typedef struct sphb_params {
+    float R;            /* :11  initial spacing                                   */
+    float H;            /* :12  smoothing length, R*1.3f                          */
+    float width;        /* :13                                                    */
+    float height;       /* :14                                                    */
+    float rho0;         /* :15  1000                                              */
+    float c0;           /* :16  400                                               */
+    float g;            /* :17  9.81 (used only by sphb_gravity_from_raw)         */
+    float dt;           /* :19  1.0f*H/C                                          */
+    float vol;          /* :20  0.57f*H*H                                         */
+    float x_min, x_max, y_min, y_max;   /* :595                                   */
+    float cell_length;  /* :596 2*H; also the search radius (:144)                */
+    int deterministic;  /* 1: inside a cell particles are kept in ascending original
+                              index, i.e. the reference's list order (:110-123), so sums
+                              run in the reference's order and results are run-to-run
+                              reproducible.  0: in-cell order is whatever the atomic
+                              counting sort produced.                              */
+    int device;         /* CUDA device ordinal                                    */
+    int reserved[6];
+} sphb_params;
+
+typedef struct sphb_stats {
+    double mass;            /* sum m                                              */
+    double mom_x, mom_y;    /* sum m*u, sum m*v                                   */
+    double kinetic;         /* 0.5 * sum m*(u^2+v^2)                              */
+    float max_speed;        /* :667-671                                           */
+    float max_rho_err;      /* max(rho - rho0) — the quantity :657-659 means to compute */
+    float last_rho_err_ref; /* what :657-659 actually computes     */
+    float min_rho, max_rho;
+    unsigned int n_escaped;         /* particles binned by clamping (reference: UB, :111-116) */
+    unsigned int max_cell_count;    /* largest cell population at the last build    */
+    unsigned int n_fluid, n_boundary;
+    unsigned long long steps;
+} sphb_stats;
+
+typedef struct sphb_ctx sphb_ctx;
+
+/* ---- resident tier -------------------------------------------------------------- */
+
+/* Fills *prm exactly as the reference's #defines evaluate (:11-21, :595-596) for the
+ * given spacing and tank; deterministic = 1, device = 0. */
+int sphb_default_params(sphb_params *prm, float R, float width, float height);
+
+int sphb_create(const sphb_params *prm, sphb_ctx **out);
+int sphb_destroy(sphb_ctx *ctx);
+
+/* Replaces the malloc'd host arrays of :491-493, :519 as the simulation state.  Copies
+ * both arrays to HBM (AoS -> SoA).  boundary may be NULL / n_boundary 0. */
+int sphb_upload(sphb_ctx *ctx, const sphb_particle *fluid, int n_fluid,
+                const sphb_particle *boundary, int n_boundary);
+
+/* :600-601  update_neighbors_context(ctx_boundary) + calculate_boundary_pseudomass */
+int sphb_init_boundary(sphb_ctx *ctx);
+
+/* :604-607  update_neighbors_context(ctx_fluid) + calculate_density +
+ * calculate_particle_pressure + calculate_accelerations on the state as it is */
+int sphb_compute_accel(sphb_ctx *ctx, float gravity_x, float gravity_y);
+
+/* :612-641  nsteps iterations of the leapfrog body (kick, drift, grid rebuild, density,
+ * pressure, accelerations, kick) with constant gravity.  Asynchronous on the handle's
+ * stream; sphb_download / sphb_stats / sphb_synchronize wait for it. */
+int sphb_step(sphb_ctx *ctx, float gravity_x, float gravity_y, int nsteps);
+
+/* Same, reading one (gx, gy) pair per step from host memory — the per-step value the
+ * reference's OpenMP threads read from `g` at :632. */
+int sphb_step_trace(sphb_ctx *ctx, const float *gravity_xy, int nsteps);
+
+/* Copies the state back in ORIGINAL particle order.  Any pointer may be NULL. */
+int sphb_download(sphb_ctx *ctx, sphb_particle *fluid_out, float *du_dt, float *dv_dt);
+int sphb_download_boundary(sphb_ctx *ctx, sphb_particle *boundary_out);
+
+/* :649 / :380-411  draw_metaballs into the SSD1306 page layout (1024 bytes). */
+int sphb_render(sphb_ctx *ctx, unsigned char *draw_buffer);
+
+/* :656-675 as device reductions, plus conservation sums. */
+int sphb_get_stats(sphb_ctx *ctx, sphb_stats *out);
+
+int sphb_synchronize(sphb_ctx *ctx);
+
+/* :439-440  raw MPU6050 counts -> gravity vector */
+int sphb_gravity_from_raw(const sphb_params *prm, int accel_x_raw, int accel_y_raw,
+                          float *gravity_x, float *gravity_y);
+
+/* ---- parity / inspection helpers (not on the hot path) ---------------------------- */
+
+/* cell index row*m_cells+col (:111-113) of every fluid particle, original order */
+int sphb_cell_ids(sphb_ctx *ctx, int *cell_out);
+int sphb_grid_shape(sphb_ctx *ctx, int *n_cells_rows, int *m_cells_cols);
+
+/* Neighbour sets as find_neighbors (:126-153) would return them for the current state.
+ * which = 0: fluid-fluid, 1: fluid-boundary, 2: boundary-boundary.  For particle i
+ * (original index) counts[i] neighbours are written to lists[i*cap ...] as ORIGINAL
+ * indices in this library's visiting order (== the reference's order when
+ * deterministic = 1).  Returns the number of particles whose count exceeded cap. */
+int sphb_neighbor_lists(sphb_ctx *ctx, int which, int cap, int *counts, int *lists);
+
+/* ---- measurement hooks --------------------------------------------------------------- */
+
+enum { SPHB_K_ADVECT_BIN = 0, SPHB_K_SCAN, SPHB_K_REORDER, SPHB_K_DENSITY, SPHB_K_FORCE,
+       SPHB_K_OTHER, SPHB_K_COUNT };
+
+/* mode 0: off.  mode 1: CUDA events around every kernel of sphb_step (accumulated). */
+int sphb_profile(sphb_ctx *ctx, int mode);
+/* Accumulated device milliseconds and launch counts per kernel class since the last
+ * reset; pair statistics of the last density pass when collected. */
+int sphb_profile_read(sphb_ctx *ctx, double ms[SPHB_K_COUNT], unsigned long long launches[SPHB_K_COUNT], int reset);
+/* candidate / accepted fluid-fluid pairs per particle for the current state (SURVEY.md
+ * §8d: C and P, "measured by the run") */
+int sphb_pair_stats(sphb_ctx *ctx, double *candidates_per_particle, double *accepted_per_particle);
+/* Evicts L2 between timed iterations: overwrites a 256 MiB scratch buffer (> the 126 MB L2)
+ * on the handle's stream.  Not part of any step. */
+int sphb_flush_l2(sphb_ctx *ctx);
+/* the cudaStream_t the handle launches on, for event timing by the caller */
+void *sphb_stream(sphb_ctx *ctx);
+/* number of kernels launched by this handle so far */
+unsigned long long sphb_launch_count(sphb_ctx *ctx);
+const char *sphb_last_error(void);
+const char *sphb_build_info(void);
+
+/* ---- compat tier: the reference's operator signatures ------------------------------- */
+
+struct particle;            /* == sphb_particle; the reference's name, :26 */
+struct neighbors_context;   /* opaque here; the reference's struct is :73-80 */
+
+struct neighbors_context *alloc_neighbors_context(int n_particles, float x_min, float x_max,
+                                                  float y_min, float y_max, float cell_length);   /* :82  */
+void update_neighbors_context(struct neighbors_context *ctx, struct particle *particles);          /* :104 */
+void calculate_boundary_pseudomass(struct particle *boundary, struct neighbors_context *ctx_boundary); /* :242 */
+void calculate_density(struct particle *fluid, struct particle *boundary,
+                       struct neighbors_context *ctx_fluid, struct neighbors_context *ctx_boundary); /* :263 */
+void calculate_particle_pressure(struct particle *particles, int n_particles);                     /* :294 */
+void calculate_accelerations(float *du_dt_fluid, float *dv_dt_fluid, struct particle *fluid,
+                             struct particle *boundary, struct neighbors_context *ctx_fluid,
+                             struct neighbors_context *ctx_boundary, float gravity_x, float gravity_y); /* :303 */
+void draw_metaballs(unsigned char *draw_buffer, struct particle *pixel_pseudoparticles,
+                    struct particle *fluid, struct neighbors_context *ctx_fluid);                    /* :380 */
+
+/* The reference fixes R/H/RHO_0/C as macros; the compat operators take them from here
+ * (default: sphb_default_params(0.075, 4, 2), H re-derived as cell_length/2 per context). */
+int sphb_compat_set_params(const sphb_params *prm);
+void sphb_compat_free_context(struct neighbors_context *ctx);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */

@@ -1,0 +1,347 @@
+"""ctypes binding of include/sph_b200.h and include/sph_b200_scene.h.
+
+``Simulation`` wraps the resident tier (what the reference's main loop would call);
+``compat`` exposes the seven reference-named operators (pi_sph_fluid.c:82-411) with the
+reference's argument meaning, operating in place on numpy arrays of ``PARTICLE`` records.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+
+#: `struct particle`, pi_sph_fluid.c:26-31 — 7 x f32 = 28 bytes
+PARTICLE = np.dtype(
+    [("x", "f4"), ("y", "f4"), ("u", "f4"), ("v", "f4"), ("m", "f4"), ("rho", "f4"), ("p", "f4")]
+)
+assert PARTICLE.itemsize == 28
+
+KERNEL_NAMES = ["advect_bin", "scan", "reorder", "density", "force", "other"]
+
+
+class SphbError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """sphb_params (include/sph_b200.h)."""
+    _fields_ = [
+        ("R", C.c_float), ("H", C.c_float), ("width", C.c_float), ("height", C.c_float),
+        ("rho0", C.c_float), ("c0", C.c_float), ("g", C.c_float), ("dt", C.c_float),
+        ("vol", C.c_float),
+        ("x_min", C.c_float), ("x_max", C.c_float), ("y_min", C.c_float), ("y_max", C.c_float),
+        ("cell_length", C.c_float), ("deterministic", C.c_int), ("device", C.c_int),
+        ("reserved", C.c_int * 6),
+    ]
+
+
+class Stats(C.Structure):
+    """sphb_stats (include/sph_b200.h)."""
+    _fields_ = [
+        ("mass", C.c_double), ("mom_x", C.c_double), ("mom_y", C.c_double), ("kinetic", C.c_double),
+        ("max_speed", C.c_float), ("max_rho_err", C.c_float), ("last_rho_err_ref", C.c_float),
+        ("min_rho", C.c_float), ("max_rho", C.c_float),
+        ("n_escaped", C.c_uint), ("max_cell_count", C.c_uint), ("n_fluid", C.c_uint),
+        ("n_boundary", C.c_uint), ("steps", C.c_ulonglong),
+    ]
+
+    def asdict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_LIB = None
+
+
+def lib_path() -> Path:
+    return PKG / "libsphb200.so"
+
+
+def lib() -> C.CDLL:
+    """Load libsphb200.so (built in-tree by ``python -m pi_sph_fluid_b200.build``)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not path.exists():
+        raise SphbError(f"{path} is missing: build it with `python -m pi_sph_fluid_b200.build` "
+                        "(there is no fallback implementation)")
+    L = C.CDLL(str(path))
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    sig = {
+        "sphb_default_params": (ci, [vp, cf, cf, cf]),
+        "sphb_create": (ci, [vp, C.POINTER(vp)]),
+        "sphb_destroy": (ci, [vp]),
+        "sphb_upload": (ci, [vp, vp, ci, vp, ci]),
+        "sphb_init_boundary": (ci, [vp]),
+        "sphb_compute_accel": (ci, [vp, cf, cf]),
+        "sphb_step": (ci, [vp, cf, cf, ci]),
+        "sphb_step_trace": (ci, [vp, vp, ci]),
+        "sphb_download": (ci, [vp, vp, vp, vp]),
+        "sphb_download_boundary": (ci, [vp, vp]),
+        "sphb_render": (ci, [vp, vp]),
+        "sphb_get_stats": (ci, [vp, vp]),
+        "sphb_synchronize": (ci, [vp]),
+        "sphb_gravity_from_raw": (ci, [vp, ci, ci, vp, vp]),
+        "sphb_cell_ids": (ci, [vp, vp]),
+        "sphb_grid_shape": (ci, [vp, vp, vp]),
+        "sphb_neighbor_lists": (ci, [vp, ci, ci, vp, vp]),
+        "sphb_profile": (ci, [vp, ci]),
+        "sphb_profile_read": (ci, [vp, vp, vp, ci]),
+        "sphb_pair_stats": (ci, [vp, vp, vp]),
+        "sphb_flush_l2": (ci, [vp]),
+        "sphb_stream": (vp, [vp]),
+        "sphb_launch_count": (C.c_ulonglong, [vp]),
+        "sphb_last_error": (C.c_char_p, []),
+        "sphb_build_info": (C.c_char_p, []),
+        "sphb_compat_set_params": (ci, [vp]),
+        "sphb_compat_free_context": (None, [vp]),
+        "alloc_neighbors_context": (vp, [ci, cf, cf, cf, cf, cf]),
+        "update_neighbors_context": (None, [vp, vp]),
+        "calculate_boundary_pseudomass": (None, [vp, vp]),
+        "calculate_density": (None, [vp, vp, vp, vp]),
+        "calculate_particle_pressure": (None, [vp, ci]),
+        "calculate_accelerations": (None, [vp, vp, vp, vp, vp, vp, cf, cf]),
+        "draw_metaballs": (None, [vp, vp, vp, vp]),
+        "sphb_scene_count_drop": (ci, [vp]),
+        "sphb_scene_fill_drop": (ci, [vp, vp]),
+        "sphb_scene_count_block": (ci, [vp, cf, cf, cf, cf]),
+        "sphb_scene_fill_block": (ci, [vp, cf, cf, cf, cf, vp]),
+        "sphb_scene_count_boundary": (ci, [vp]),
+        "sphb_scene_fill_boundary": (ci, [vp, vp]),
+        "sphb_gravity_trace_tilt": (ci, [vp, cf, ci, ci, ci, vp]),
+        "sphb_spacing_for_count": (cf, [C.c_double, C.c_double]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+def _check(rc: int, what: str) -> int:
+    if rc < 0:
+        raise SphbError(f"{what} failed ({rc}): {lib().sphb_last_error().decode()}")
+    return rc
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _particles(a: np.ndarray) -> np.ndarray:
+    if a.dtype != PARTICLE or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("expected a C-contiguous array of PARTICLE records")
+    return a
+
+
+def default_params(R: float = 0.075, width: float = 4.0, height: float = 2.0,
+                   deterministic: bool = True, device: int = 0) -> Params:
+    prm = Params()
+    _check(lib().sphb_default_params(C.byref(prm), R, width, height), "sphb_default_params")
+    prm.deterministic = int(deterministic)
+    prm.device = device
+    return prm
+
+
+# ------------------------------------------------------------------------------- scenes
+
+def scene_drop(prm: Params) -> np.ndarray:
+    """The reference's initial drop, pi_sph_fluid.c:484-506."""
+    n = _check(lib().sphb_scene_count_drop(C.byref(prm)), "sphb_scene_count_drop")
+    a = np.zeros(n, PARTICLE)
+    _check(lib().sphb_scene_fill_drop(C.byref(prm), _p(a)), "sphb_scene_fill_drop")
+    return a
+
+
+def scene_block(prm: Params, x0: float, x1: float, y0: float, y1: float) -> np.ndarray:
+    n = _check(lib().sphb_scene_count_block(C.byref(prm), x0, x1, y0, y1), "sphb_scene_count_block")
+    a = np.zeros(n, PARTICLE)
+    _check(lib().sphb_scene_fill_block(C.byref(prm), x0, x1, y0, y1, _p(a)), "sphb_scene_fill_block")
+    return a
+
+
+def scene_boundary(prm: Params) -> np.ndarray:
+    """The reference's four walls, pi_sph_fluid.c:513-540."""
+    n = _check(lib().sphb_scene_count_boundary(C.byref(prm)), "sphb_scene_count_boundary")
+    a = np.zeros(n, PARTICLE)
+    _check(lib().sphb_scene_fill_boundary(C.byref(prm), _p(a)), "sphb_scene_fill_boundary")
+    return a
+
+
+def gravity_from_raw(prm: Params, ax_raw: int, ay_raw: int):
+    gx, gy = C.c_float(), C.c_float()
+    _check(lib().sphb_gravity_from_raw(C.byref(prm), ax_raw, ay_raw, C.byref(gx), C.byref(gy)), "sphb_gravity_from_raw")
+    return np.float32(gx.value), np.float32(gy.value)
+
+
+def gravity_trace_tilt(prm: Params, amplitude_deg: float, period_steps: int, hold_steps: int, nsteps: int) -> np.ndarray:
+    out = np.zeros((nsteps, 2), np.float32)
+    _check(lib().sphb_gravity_trace_tilt(C.byref(prm), amplitude_deg, period_steps, hold_steps, nsteps, _p(out)),
+           "sphb_gravity_trace_tilt")
+    return out
+
+
+def spacing_for_count(area: float, n_target: float) -> float:
+    return float(lib().sphb_spacing_for_count(area, n_target))
+
+
+# ------------------------------------------------------------------------------- resident tier
+
+class Simulation:
+    """Resident-tier handle: the state of the reference's main() kept in HBM."""
+
+    def __init__(self, prm: Params | None = None, **kw):
+        self.prm = prm if prm is not None else default_params(**kw)
+        self._h = C.c_void_p()
+        _check(lib().sphb_create(C.byref(self.prm), C.byref(self._h)), "sphb_create")
+        self.n_fluid = 0
+        self.n_boundary = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sphb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # :491-547 arrays -> HBM
+    def upload(self, fluid: np.ndarray, boundary: np.ndarray | None = None):
+        nb = 0 if boundary is None else len(boundary)
+        _check(lib().sphb_upload(self._h, _p(_particles(fluid)), len(fluid),
+                                 _p(_particles(boundary)) if nb else None, nb), "sphb_upload")
+        self.n_fluid, self.n_boundary = len(fluid), nb
+
+    def init_boundary(self):                       # :600-601
+        _check(lib().sphb_init_boundary(self._h), "sphb_init_boundary")
+
+    def compute_accel(self, gx: float = 0.0, gy: float = -9.81):   # :604-607
+        _check(lib().sphb_compute_accel(self._h, gx, gy), "sphb_compute_accel")
+
+    def step(self, nsteps: int = 1, gx: float = 0.0, gy: float = -9.81):   # :612-641
+        _check(lib().sphb_step(self._h, gx, gy, nsteps), "sphb_step")
+
+    def step_trace(self, gravity_xy: np.ndarray):
+        g = np.ascontiguousarray(gravity_xy, np.float32)
+        assert g.ndim == 2 and g.shape[1] == 2
+        _check(lib().sphb_step_trace(self._h, _p(g), len(g)), "sphb_step_trace")
+
+    def synchronize(self):
+        _check(lib().sphb_synchronize(self._h), "sphb_synchronize")
+
+    def download(self, accel: bool = True):
+        fluid = np.zeros(self.n_fluid, PARTICLE)
+        du = np.zeros(self.n_fluid, np.float32) if accel else None
+        dv = np.zeros(self.n_fluid, np.float32) if accel else None
+        _check(lib().sphb_download(self._h, _p(fluid), _p(du), _p(dv)), "sphb_download")
+        return (fluid, du, dv) if accel else fluid
+
+    def download_into(self, fluid: np.ndarray, du: np.ndarray | None, dv: np.ndarray | None):
+        _check(lib().sphb_download(self._h, _p(_particles(fluid)), _p(du), _p(dv)), "sphb_download")
+
+    def download_boundary(self) -> np.ndarray:
+        b = np.zeros(self.n_boundary, PARTICLE)
+        _check(lib().sphb_download_boundary(self._h, _p(b)), "sphb_download_boundary")
+        return b
+
+    def render(self) -> np.ndarray:                # :649
+        buf = np.zeros(1024, np.uint8)
+        _check(lib().sphb_render(self._h, _p(buf)), "sphb_render")
+        return buf
+
+    def stats(self) -> dict:                       # :656-675
+        st = Stats()
+        _check(lib().sphb_get_stats(self._h, C.byref(st)), "sphb_get_stats")
+        return st.asdict()
+
+    def grid_shape(self):
+        r, c = C.c_int(), C.c_int()
+        _check(lib().sphb_grid_shape(self._h, C.byref(r), C.byref(c)), "sphb_grid_shape")
+        return r.value, c.value
+
+    def cell_ids(self) -> np.ndarray:
+        out = np.zeros(self.n_fluid, np.int32)
+        _check(lib().sphb_cell_ids(self._h, _p(out)), "sphb_cell_ids")
+        return out
+
+    def neighbor_lists(self, which: int = 0, cap: int = 64):
+        n = self.n_boundary if which == 2 else self.n_fluid
+        counts = np.zeros(n, np.int32)
+        lists = np.zeros((n, cap), np.int32)
+        over = _check(lib().sphb_neighbor_lists(self._h, which, cap, _p(counts), _p(lists)), "sphb_neighbor_lists")
+        return counts, lists, over
+
+    def pair_stats(self):
+        c, a = C.c_double(), C.c_double()
+        _check(lib().sphb_pair_stats(self._h, C.byref(c), C.byref(a)), "sphb_pair_stats")
+        return c.value, a.value
+
+    def profile(self, mode: int):
+        _check(lib().sphb_profile(self._h, mode), "sphb_profile")
+
+    def profile_read(self, reset: bool = True) -> dict:
+        ms = (C.c_double * len(KERNEL_NAMES))()
+        ln = (C.c_ulonglong * len(KERNEL_NAMES))()
+        _check(lib().sphb_profile_read(self._h, ms, ln, int(reset)), "sphb_profile_read")
+        return {k: {"ms": ms[i], "launches": int(ln[i])} for i, k in enumerate(KERNEL_NAMES)}
+
+    def flush_l2(self):
+        _check(lib().sphb_flush_l2(self._h), "sphb_flush_l2")
+
+    @property
+    def stream(self) -> int:
+        return int(lib().sphb_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().sphb_launch_count(self._h))
+
+
+# ------------------------------------------------------------------------------- compat tier
+
+class _Compat:
+    """The reference's operator functions (pi_sph_fluid.c), same names, same argument order;
+    arrays are numpy ``PARTICLE`` records modified in place exactly where the reference
+    writes them."""
+
+    def set_params(self, prm: Params):
+        _check(lib().sphb_compat_set_params(C.byref(prm)), "sphb_compat_set_params")
+
+    def alloc_neighbors_context(self, n_particles, x_min, x_max, y_min, y_max, cell_length):    # :82
+        return C.c_void_p(lib().alloc_neighbors_context(n_particles, x_min, x_max, y_min, y_max, cell_length))
+
+    def free_neighbors_context(self, ctx):
+        lib().sphb_compat_free_context(ctx)
+
+    def update_neighbors_context(self, ctx, particles):                                         # :104
+        lib().update_neighbors_context(ctx, _p(_particles(particles)))
+
+    def calculate_boundary_pseudomass(self, boundary, ctx_boundary):                            # :242
+        lib().calculate_boundary_pseudomass(_p(_particles(boundary)), ctx_boundary)
+
+    def calculate_density(self, fluid, boundary, ctx_fluid, ctx_boundary):                      # :263
+        lib().calculate_density(_p(_particles(fluid)), _p(_particles(boundary)), ctx_fluid, ctx_boundary)
+
+    def calculate_particle_pressure(self, particles, n_particles=None):                         # :294
+        lib().calculate_particle_pressure(_p(_particles(particles)), len(particles) if n_particles is None else n_particles)
+
+    def calculate_accelerations(self, du_dt, dv_dt, fluid, boundary, ctx_fluid, ctx_boundary, gravity_x, gravity_y):   # :303
+        assert du_dt.dtype == np.float32 and dv_dt.dtype == np.float32
+        lib().calculate_accelerations(_p(du_dt), _p(dv_dt), _p(_particles(fluid)), _p(_particles(boundary)),
+                                      ctx_fluid, ctx_boundary, gravity_x, gravity_y)
+
+    def draw_metaballs(self, draw_buffer, pixel_pseudoparticles, fluid, ctx_fluid):            # :380
+        assert draw_buffer.dtype == np.uint8 and draw_buffer.size == 1024
+        lib().draw_metaballs(_p(draw_buffer), _p(_particles(pixel_pseudoparticles)), _p(_particles(fluid)), ctx_fluid)
+
+
+compat = _Compat()

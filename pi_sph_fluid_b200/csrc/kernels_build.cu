@@ -1,0 +1,374 @@
+// kernels_build.cu — the counting-sort cell build that replaces the reference's serial
+// linked-list rebuild (update_neighbors_context, pi_sph_fluid.c:104-124), fused with the
+// leapfrog kick + drift loops that precede it in the step (:615-624), plus the AoS<->SoA
+// converters at the host boundary.
+//
+//   k_advect_bin   u,v += 0.5*DT*a (double) ; x,y += DT*u ; cell = (int)((y-ymin)/cell)*m + ...
+//                  ; rank = atomicAdd(count[cell])                       HBM-bound, 44 B/particle
+//   k_scan         exclusive prefix sum of count[] -> start[] (single pass, decoupled
+//                  look-back, warp-shuffle scans), re-zeroing count[]    HBM-bound, 8 B/cell
+//   k_scatter_ids  (deterministic mode) ids into their cell's range in arrival order
+//   k_reorder      dst = start[cell] + rank, rank = #ids in the cell below mine
+//                  (deterministic: the reference's ascending-index list order, :110-123)
+//                  or the atomic's arrival rank; moves pos/vel/id        HBM-bound, 40-56 B/particle
+#include "sphb_internal.cuh"
+
+namespace sphb {
+
+// ------------------------------------------------------------------------ advect + bin
+
+template <bool ADVECT>
+__global__ void __launch_bounds__(kStreamThreads)
+k_advect_bin(const Consts k, const int n, float2 *__restrict__ pos, float2 *__restrict__ vel,
+             const float2 *__restrict__ acc, uint32_t *__restrict__ key, uint32_t *__restrict__ rank,
+             uint32_t *__restrict__ cell_count, DeviceCounters *__restrict__ ctr)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (s >= n) return;
+    float2 p = pos[s];
+    if (ADVECT) {
+        float2 v = vel[s];
+        const float2 a = acc[s];
+        v.x = kick(k, v.x, a.x);          // :616
+        v.y = kick(k, v.y, a.y);          // :617
+        p.x = drift(k, p.x, v.x);         // :622
+        p.y = drift(k, p.y, v.y);         // :623
+        vel[s] = v;
+        pos[s] = p;
+    }
+    int row, col;
+    bool clamped;
+    cell_of(k, p.x, p.y, row, col, clamped);          // :111-112
+    if (clamped) atomicAdd(&ctr->n_escaped, 1u);
+    const uint32_t c = (uint32_t)(row * k.cols + col);   // :113
+    key[s] = c;
+    rank[s] = atomicAdd(&cell_count[c], 1u);
+}
+
+int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool advect, DeviceCounters *ctr)
+{
+    if (ps.n == 0) return 0;
+    const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
+    if (advect)
+        k_advect_bin<true><<<grid, kStreamThreads, 0, st>>>(k, ps.n, ps.pos[ps.pc], ps.vel[ps.vc], ps.acc,
+                                                            ps.key, ps.rank, ps.cell_count, ctr);
+    else
+        k_advect_bin<false><<<grid, kStreamThreads, 0, st>>>(k, ps.n, ps.pos[ps.pc], ps.vel[ps.vc], ps.acc,
+                                                             ps.key, ps.rank, ps.cell_count, ctr);
+    return 1;
+}
+
+// ------------------------------------------------------------------------ scan
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr unsigned int kFlagAggregate = 1u, kFlagPrefix = 2u;
+__device__ __forceinline__ unsigned long long pack_state(unsigned int epoch, unsigned int flag, uint32_t value)
+{
+    return ((unsigned long long)((epoch << 2) | flag) << 32) | value;
+}
+
+// One tile = kScanTile counters.  Tile ids are handed out by an atomic so a tile only ever
+// waits on tiles that already started (forward progress without relying on block order).
+__global__ void __launch_bounds__(kScanThreads)
+k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
+       unsigned long long *__restrict__ tile_state, unsigned long long *__restrict__ tile_counter,
+       const unsigned long long counter_base, const unsigned int epoch, const int n_tiles,
+       DeviceCounters *__restrict__ ctr)
+{
+    __shared__ uint32_t s_warp_sum[kScanThreads / 32];
+    __shared__ uint32_t s_warp_max[kScanThreads / 32];
+    __shared__ uint32_t s_tile, s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (uint32_t)(atomicAdd(tile_counter, 1ULL) - counter_base);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const long long base = (long long)tile * kScanTile + (long long)tid * kScanItems;
+
+    uint32_t v[kScanItems];
+    if (base + kScanItems <= n) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(count + base);
+        const uint4 b = *reinterpret_cast<const uint4 *>(count + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) v[i] = (base + i < n) ? count[base + i] : 0u;
+    }
+    uint32_t tsum = 0, tmax = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        const uint32_t c = v[i];
+        v[i] = tsum;                 // exclusive within the thread
+        tsum += c;
+        tmax = c > tmax ? c : tmax;
+    }
+    // warp inclusive scan of thread sums
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, tmax, d);
+        tmax = o > tmax ? o : tmax;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    if (lane == 0) s_warp_max[warp] = tmax;
+    __syncthreads();
+    uint32_t warp_excl = 0, aggregate = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++) {
+        const uint32_t ws = s_warp_sum[w];
+        if (w < warp) warp_excl += ws;
+        aggregate += ws;
+    }
+
+    if (warp == 0) {
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_volatile_u64(&tile_state[0], pack_state(epoch, kFlagPrefix, aggregate));
+        } else {
+            if (lane == 0) st_volatile_u64(&tile_state[tile], pack_state(epoch, kFlagAggregate, aggregate));
+            int look = (int)tile - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long st;
+                bool invalid;
+                do {
+                    st = idx >= 0 ? ld_volatile_u64(&tile_state[idx]) : pack_state(epoch, kFlagPrefix, 0u);
+                    const unsigned int hi = (unsigned int)(st >> 32);
+                    invalid = ((hi >> 2) != epoch) || ((hi & 3u) == 0u);
+                } while (__any_sync(0xffffffffu, invalid));
+                const bool is_prefix = (((unsigned int)(st >> 32)) & 3u) == kFlagPrefix;
+                const unsigned int mask = __ballot_sync(0xffffffffu, is_prefix);
+                const int first = mask ? (__ffs(mask) - 1) : 32;
+                uint32_t contrib = (lane <= first) ? (uint32_t)st : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                excl += contrib;
+                if (mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_volatile_u64(&tile_state[tile], pack_state(epoch, kFlagPrefix, excl + aggregate));
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            uint32_t m = 0;
+#pragma unroll
+            for (int w = 0; w < kScanThreads / 32; w++) m = s_warp_max[w] > m ? s_warp_max[w] : m;
+            if (m) atomicMax(&ctr->max_cell_count, m);
+            if ((int)tile == n_tiles - 1) start[n] = excl + aggregate;
+        }
+    }
+    __syncthreads();
+    const uint32_t off = s_prefix + warp_excl + (incl - tsum);
+    if (base + kScanItems <= n) {
+        *reinterpret_cast<uint4 *>(start + base) = make_uint4(off + v[0], off + v[1], off + v[2], off + v[3]);
+        *reinterpret_cast<uint4 *>(start + base + 4) = make_uint4(off + v[4], off + v[5], off + v[6], off + v[7]);
+        *reinterpret_cast<uint4 *>(count + base) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(count + base + 4) = make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++)
+            if (base + i < n) { start[base + i] = off + v[i]; count[base + i] = 0u; }
+    }
+}
+
+int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc, DeviceCounters *ctr)
+{
+    const int n_tiles = (k.ncells + kScanTile - 1) / kScanTile;
+    sc.epoch = (sc.epoch + 1) & 0x3fffffffu;
+    if (sc.epoch == 0) sc.epoch = 1;   // 0 is the memset state ("never written")
+    const unsigned long long base = sc.launches;   // tiles handed out so far
+    k_scan<<<n_tiles, kScanThreads, 0, st>>>(ps.cell_count, ps.cell_start, k.ncells, sc.tile_state,
+                                             sc.tile_counter, base, sc.epoch, n_tiles, ctr);
+    sc.launches += (unsigned long long)n_tiles;
+    return 1;
+}
+
+// ------------------------------------------------------------------------ reorder
+
+__global__ void __launch_bounds__(kStreamThreads)
+k_scatter_ids(const int n, const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
+              const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ start,
+              uint32_t *__restrict__ ids_tmp)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (s >= n) return;
+    ids_tmp[start[key[s]] + rank[s]] = id_in[s];
+}
+
+template <bool DET, bool MASS, bool AUX>
+__global__ void __launch_bounds__(kStreamThreads)
+k_reorder(const int n, const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
+          const uint32_t *__restrict__ start, const uint32_t *__restrict__ ids_tmp,
+          const float2 *__restrict__ pos_in, const float2 *__restrict__ vel_in,
+          const uint32_t *__restrict__ id_in, const float *__restrict__ mass_in,
+          const float *__restrict__ aux_in, float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
+          uint32_t *__restrict__ id_out, float *__restrict__ mass_out, float *__restrict__ aux_out)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t c = key[s];
+    const uint32_t my = id_in[s];
+    const uint32_t b = start[c];
+    uint32_t dst;
+    if (DET) {
+        // rank = number of ids in my cell smaller than mine -> ascending original index,
+        // the order the reference's tail-append produces (:110-123)
+        const uint32_t e = start[c + 1];
+        uint32_t r = 0;
+        for (uint32_t j = b; j < e; j++) r += (ids_tmp[j] < my) ? 1u : 0u;
+        dst = b + r;
+    } else {
+        dst = b + rank[s];
+    }
+    pos_out[dst] = pos_in[s];
+    vel_out[dst] = vel_in[s];
+    id_out[dst] = my;
+    if (MASS) mass_out[dst] = mass_in[s];
+    if (AUX) aux_out[dst] = aux_in[s];
+}
+
+int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deterministic)
+{
+    (void)k;
+    if (ps.n == 0) return 0;
+    const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
+    int launches = 0;
+    if (deterministic) {
+        k_scatter_ids<<<grid, kStreamThreads, 0, st>>>(ps.n, ps.key, ps.rank, ps.id[ps.ic], ps.cell_start, ps.ids_tmp);
+        launches++;
+    }
+    const bool has_mass = ps.mass[0] != nullptr;
+    const bool has_aux = ps.aux[0] != nullptr;
+    const float *mass_in = has_mass ? ps.mass[ps.mc] : nullptr;
+    float *mass_out = has_mass ? ps.mass[ps.mc ^ 1] : nullptr;
+    const float *aux_in = has_aux ? ps.aux[ps.xc] : nullptr;
+    float *aux_out = has_aux ? ps.aux[ps.xc ^ 1] : nullptr;
+#define SPHB_REORDER(D, M, A)                                                                           \
+    k_reorder<D, M, A><<<grid, kStreamThreads, 0, st>>>(ps.n, ps.key, ps.rank, ps.cell_start, ps.ids_tmp, \
+        ps.pos[ps.pc], ps.vel[ps.vc], ps.id[ps.ic], mass_in, aux_in, ps.pos[ps.pc ^ 1],                  \
+        ps.vel[ps.vc ^ 1], ps.id[ps.ic ^ 1], mass_out, aux_out)
+    if (deterministic) {
+        if (has_mass && has_aux) SPHB_REORDER(true, true, true);
+        else if (has_mass) SPHB_REORDER(true, true, false);
+        else if (has_aux) SPHB_REORDER(true, false, true);
+        else SPHB_REORDER(true, false, false);
+    } else {
+        if (has_mass && has_aux) SPHB_REORDER(false, true, true);
+        else if (has_mass) SPHB_REORDER(false, true, false);
+        else if (has_aux) SPHB_REORDER(false, false, true);
+        else SPHB_REORDER(false, false, false);
+    }
+#undef SPHB_REORDER
+    launches++;
+    ps.pc ^= 1; ps.vc ^= 1; ps.ic ^= 1;
+    if (has_mass) ps.mc ^= 1;
+    if (has_aux) ps.xc ^= 1;
+    ps.sorted = true;
+    return launches;
+}
+
+// ------------------------------------------------------------------------ host boundary
+
+// AoS `struct particle` (:26-31) -> SoA, identity order
+__global__ void __launch_bounds__(kStreamThreads)
+k_aos_to_soa(const int n, const float *__restrict__ aos, float2 *__restrict__ pos, float2 *__restrict__ vel,
+             uint32_t *__restrict__ id, float *__restrict__ mass, float *__restrict__ aux,
+             float2 *__restrict__ rho_prr, float *__restrict__ p, float2 *__restrict__ acc)
+{
+    const int i = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (i >= n) return;
+    const float *r = aos + (size_t)i * 7;
+    pos[i] = make_float2(r[0], r[1]);
+    vel[i] = make_float2(r[2], r[3]);
+    id[i] = (uint32_t)i;
+    if (mass) mass[i] = r[4];
+    if (aux) aux[i] = r[5];
+    if (rho_prr) rho_prr[i] = make_float2(r[5], 0.0f);
+    if (p) p[i] = r[6];
+    if (acc) acc[i] = make_float2(0.0f, 0.0f);
+}
+
+int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, bool is_boundary)
+{
+    if (ps.n == 0) return 0;
+    const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
+    ps.pc = ps.vc = ps.ic = ps.mc = ps.xc = 0;
+    k_aos_to_soa<<<grid, kStreamThreads, 0, st>>>(ps.n, reinterpret_cast<const float *>(aos), ps.pos[0], ps.vel[0],
+                                                  ps.id[0], ps.mass[0], is_boundary ? ps.aux[0] : nullptr,
+                                                  is_boundary ? nullptr : ps.rho_prr, is_boundary ? nullptr : ps.p,
+                                                  is_boundary ? nullptr : ps.acc);
+    ps.sorted = false;
+    return 1;
+}
+
+// SoA (sorted) -> AoS in ORIGINAL order via id[]
+__global__ void __launch_bounds__(kStreamThreads)
+k_soa_to_aos(const int n, const float2 *__restrict__ pos, const float2 *__restrict__ vel,
+             const uint32_t *__restrict__ id, const float *__restrict__ mass, const float uniform_mass,
+             const float *__restrict__ aux, const float2 *__restrict__ rho_prr, const float *__restrict__ p,
+             const float2 *__restrict__ acc, float *__restrict__ aos, float *__restrict__ du,
+             float *__restrict__ dv)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t i = id[s];
+    if (aos) {
+        float *r = aos + (size_t)i * 7;
+        const float2 x = pos[s], v = vel[s];
+        r[0] = x.x; r[1] = x.y; r[2] = v.x; r[3] = v.y;
+        r[4] = mass ? mass[s] : uniform_mass;
+        r[5] = rho_prr ? rho_prr[s].x : (aux ? aux[s] : 0.0f);
+        r[6] = p ? p[s] : 0.0f;
+    }
+    if (du) { const float2 a = acc[s]; du[i] = a.x; dv[i] = a.y; }
+}
+
+int launch_soa_to_aos(cudaStream_t st, const ParticleSet &ps, sphb_particle *aos, float *du, float *dv, bool is_boundary)
+{
+    if (ps.n == 0) return 0;
+    const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
+    k_soa_to_aos<<<grid, kStreamThreads, 0, st>>>(
+        ps.n, ps.pos[ps.pc], ps.vel[ps.vc], ps.id[ps.ic], ps.mass[0] ? ps.mass[ps.mc] : nullptr,
+        ps.uniform_mass_value, is_boundary ? ps.aux[ps.xc] : nullptr, is_boundary ? nullptr : ps.rho_prr,
+        is_boundary ? nullptr : ps.p, ps.acc, reinterpret_cast<float *>(aos), is_boundary ? nullptr : du,
+        is_boundary ? nullptr : dv);
+    return 1;
+}
+
+__global__ void __launch_bounds__(kStreamThreads)
+k_cell_ids(const Consts k, const int n, const float2 *__restrict__ pos, const uint32_t *__restrict__ id,
+           int *__restrict__ cell_out)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (s >= n) return;
+    const float2 p = pos[s];
+    int row, col;
+    bool clamped;
+    cell_of(k, p.x, p.y, row, col, clamped);
+    cell_out[id[s]] = row * k.cols + col;
+}
+
+int launch_cell_ids(cudaStream_t st, const Consts &k, const ParticleSet &ps, int *cell_out)
+{
+    if (ps.n == 0) return 0;
+    const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
+    k_cell_ids<<<grid, kStreamThreads, 0, st>>>(k, ps.n, ps.pos[ps.pc], ps.id[ps.ic], cell_out);
+    return 1;
+}
+
+}  // namespace sphb

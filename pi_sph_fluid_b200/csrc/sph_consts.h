@@ -1,0 +1,57 @@
+// sph_consts.h — host-side derivation of the kernel constants (sphb::Consts) from
+// sphb_params, with the reference's expression types (pi_sph_fluid.c:11-21, :46, :144, :297,
+// :325, :332-334, :616).  Header-only so the host emulation test (tests/emu) uses the very
+// same numbers as the library.
+#pragma once
+
+#include <math.h>
+#include <string.h>
+
+#include "../../include/sph_b200.h"
+#include "sph_math.cuh"
+
+namespace sphb {
+
+// W(r,0,0,0) on the host with the reference's expression (:45-50); used only for constants.
+inline float host_W(float H, float r)
+{
+    const float nf = (float)(7 / (4 * M_PI * (double)H * (double)H));
+    const float q = r / H;
+    const float a = 1 - 0.5f * q, b = 1 + 2 * q;
+    return nf * powf(a, 4) * b;
+}
+
+inline Consts make_consts(const sphb_params &p, float uniform_mass)
+{
+    Consts k;
+    memset(&k, 0, sizeof k);
+    k.x_min = p.x_min;
+    k.y_min = p.y_min;
+    k.cell = p.cell_length;
+    k.rows = (int)((p.y_max - p.y_min) / p.cell_length) + 1;     // :93
+    k.cols = (int)((p.x_max - p.x_min) / p.cell_length) + 1;     // :94
+    k.ncells = k.rows * k.cols;
+    k.H = p.H;
+    k.inv_H = 1.0f / p.H;
+    k.support = 2 * p.H;                                          // :144
+    // largest float t with sqrtf(t) < 2*H: the test `sqrtf(d2) < 2*H` is then `d2 <= t`
+    float t = k.support * k.support;
+    while (sqrtf(t) < k.support) t = nextafterf(t, INFINITY);
+    while (!(sqrtf(t) < k.support)) t = nextafterf(t, -INFINITY);
+    k.d2max = t;
+    const double Hd = (double)p.H;
+    k.nf = (float)(7 / (4 * M_PI * Hd * Hd));                     // :46
+    k.grad_c = (float)(-5.0 * (double)k.nf / (Hd * Hd));
+    k.inv_W_ref = 1.0f / host_W(p.H, (float)(0.2 * Hd));          // :325
+    k.rho0 = p.rho0;
+    k.inv_rho0 = 1.0f / p.rho0;
+    k.B = p.c0 * p.c0 * p.rho0 / 7;                               // :297
+    k.eps_h2 = (float)(0.01 * Hd * Hd);                           // :332
+    k.visc_cH = (float)(-0.01 * (double)p.c0 * Hd);               // :332, :334
+    k.mass = uniform_mass;
+    k.dt = p.dt;
+    k.half_dt = 0.5 * (double)p.dt;                               // :616
+    return k;
+}
+
+}  // namespace sphb

@@ -1,0 +1,575 @@
+// sphb_api.cu — resident tier of the C ABI (include/sph_b200.h): owns the device state and
+// sequences the kernels of one leapfrog step exactly as the reference's main loop does
+// (pi_sph_fluid.c:600-607 init, :612-641 step).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "sphb_internal.cuh"
+#include "sph_consts.h"
+
+namespace sphb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return SPHB_E_CUDA;
+}
+
+static void free_set(ParticleSet &ps)
+{
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ps.pos[i]); cudaFree(ps.vel[i]); cudaFree(ps.id[i]); cudaFree(ps.mass[i]); cudaFree(ps.aux[i]);
+    }
+    cudaFree(ps.acc); cudaFree(ps.rho_prr); cudaFree(ps.p); cudaFree(ps.key); cudaFree(ps.rank);
+    cudaFree(ps.ids_tmp); cudaFree(ps.cell_count); cudaFree(ps.cell_start);
+    ps = ParticleSet();
+}
+
+template <class T>
+static cudaError_t dmalloc(T **p, size_t count)
+{
+    return cudaMalloc(reinterpret_cast<void **>(p), (count ? count : 1) * sizeof(T));
+}
+
+// (re)allocate a set for n particles; arrays carry 2 padding slots so 16-byte-aligned tile
+// copies may touch one element past either end of a run
+int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_mass)
+{
+    if (ps.cap >= n && ps.cell_count && (need_mass ? ps.mass[0] != nullptr : true) &&
+        (is_boundary ? ps.aux[0] != nullptr : ps.acc != nullptr)) {
+        ps.n = n;
+        return SPHB_OK;
+    }
+    free_set(ps);
+    const size_t m = (size_t)n + 4;
+    for (int i = 0; i < 2; i++) {
+        SPHB_CUDA(dmalloc(&ps.pos[i], m));
+        SPHB_CUDA(dmalloc(&ps.vel[i], m));
+        SPHB_CUDA(dmalloc(&ps.id[i], m));
+        SPHB_CUDA(cudaMemset(ps.pos[i], 0, m * sizeof(float2)));
+        SPHB_CUDA(cudaMemset(ps.vel[i], 0, m * sizeof(float2)));
+        if (need_mass) { SPHB_CUDA(dmalloc(&ps.mass[i], m)); SPHB_CUDA(cudaMemset(ps.mass[i], 0, m * sizeof(float))); }
+        if (is_boundary) SPHB_CUDA(dmalloc(&ps.aux[i], m));
+    }
+    if (!is_boundary) {
+        SPHB_CUDA(dmalloc(&ps.acc, m));
+        SPHB_CUDA(dmalloc(&ps.rho_prr, m));
+        SPHB_CUDA(dmalloc(&ps.p, m));
+        SPHB_CUDA(cudaMemset(ps.rho_prr, 0, m * sizeof(float2)));
+    }
+    SPHB_CUDA(dmalloc(&ps.key, m));
+    SPHB_CUDA(dmalloc(&ps.rank, m));
+    SPHB_CUDA(dmalloc(&ps.ids_tmp, m));
+    SPHB_CUDA(dmalloc(&ps.cell_count, (size_t)ncells + 8));
+    SPHB_CUDA(dmalloc(&ps.cell_start, (size_t)ncells + 8));
+    SPHB_CUDA(cudaMemset(ps.cell_count, 0, ((size_t)ncells + 8) * sizeof(uint32_t)));
+    SPHB_CUDA(cudaMemset(ps.cell_start, 0, ((size_t)ncells + 8) * sizeof(uint32_t)));
+    ps.n = n;
+    ps.cap = n;
+    return SPHB_OK;
+}
+
+int ensure_stage(sphb_ctx *c, size_t bytes)
+{
+    if (c->stage_bytes >= bytes) return SPHB_OK;
+    cudaFree(c->d_stage);
+    c->d_stage = nullptr;
+    c->stage_bytes = 0;
+    SPHB_CUDA(cudaMalloc(&c->d_stage, bytes));
+    c->stage_bytes = bytes;
+    return SPHB_OK;
+}
+
+// ---- profiling ------------------------------------------------------------------------
+
+static int prof_drain(sphb_ctx *c)
+{
+    if (c->ev_used == 0) return SPHB_OK;
+    SPHB_CUDA(cudaEventSynchronize(c->ev[2 * (c->ev_used - 1) + 1]));
+    for (int i = 0; i < c->ev_used; i++) {
+        float ms = 0.0f;
+        SPHB_CUDA(cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]));
+        c->prof_ms[c->ev_kind[i]] += (double)ms;
+        c->prof_launches[c->ev_kind[i]] += 1;
+    }
+    c->ev_used = 0;
+    return SPHB_OK;
+}
+
+struct ProfScope {
+    sphb_ctx *c;
+    int slot;
+    ProfScope(sphb_ctx *ctx, int kind) : c(ctx), slot(-1)
+    {
+        if (!c->profile_mode) return;
+        if (c->ev_used == 64) prof_drain(c);
+        slot = c->ev_used++;
+        c->ev_kind[slot] = kind;
+        cudaEventRecord(c->ev[2 * slot], c->stream);
+    }
+    ~ProfScope()
+    {
+        if (slot >= 0) cudaEventRecord(c->ev[2 * slot + 1], c->stream);
+    }
+};
+
+// ---- step pieces ----------------------------------------------------------------------
+
+// update_neighbors_context (:104-124) for one set, optionally fused with kick+drift
+int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect)
+{
+    { ProfScope p(c, SPHB_K_ADVECT_BIN); c->launches += launch_advect_bin(c->stream, c->k, ps, advect, c->d_counters); }
+    { ProfScope p(c, SPHB_K_SCAN); c->launches += launch_scan(c->stream, c->k, ps, c->scan, c->d_counters); }
+    { ProfScope p(c, SPHB_K_REORDER); c->launches += launch_reorder(c->stream, c->k, ps, c->prm.deterministic != 0); }
+    return SPHB_OK;
+}
+
+int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kick2)
+{
+    { ProfScope p(c, SPHB_K_DENSITY); c->launches += launch_density(c->stream, c->k, c->fluid, c->boundary, c->d_counters, false); }
+    { ProfScope p(c, SPHB_K_FORCE); c->launches += launch_force(c->stream, c->k, c->fluid, c->boundary, gx, gy, g_dev, kick2, c->d_counters); }
+    return SPHB_OK;
+}
+
+static int check_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); libsphb200 has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return SPHB_E_CUDA;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (%d devices)", device, count); return SPHB_E_ARG; }
+    cudaDeviceProp prop;
+    SPHB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return SPHB_E_CUDA;
+    }
+    return SPHB_OK;
+}
+
+}  // namespace sphb
+
+using namespace sphb;
+
+#define SPHB_ENTER(ctx)                                               \
+    do {                                                              \
+        if (!(ctx)) { set_error("null context"); return SPHB_E_ARG; } \
+        SPHB_CUDA(cudaSetDevice((ctx)->device));                      \
+    } while (0)
+
+extern "C" {
+
+const char *sphb_last_error(void) { return g_err; }
+
+const char *sphb_build_info(void)
+{
+    return "libsphb200 v1: sm_100a, nvcc " __DATE__ ", pair CTA 128 thr, tile 768, list 64";
+}
+
+int sphb_default_params(sphb_params *prm, float R, float width, float height)
+{
+    if (!prm) return SPHB_E_ARG;
+    memset(prm, 0, sizeof *prm);
+    prm->R = R;
+    prm->H = R * 1.3f;                      // :12
+    prm->width = width;
+    prm->height = height;
+    prm->rho0 = 1000.0f;
+    prm->c0 = 400.0f;
+    prm->g = 9.81f;
+    prm->dt = 1.0f * prm->H / prm->c0;      // :19
+    prm->vol = 0.57f * prm->H * prm->H;     // :20
+    prm->x_min = 0; prm->x_max = width; prm->y_min = 0; prm->y_max = height;   // :595
+    prm->cell_length = 2 * prm->H;          // :596
+    prm->deterministic = 1;
+    prm->device = 0;
+    return SPHB_OK;
+}
+
+int sphb_gravity_from_raw(const sphb_params *prm, int accel_x_raw, int accel_y_raw, float *gx, float *gy)
+{
+    if (!prm || !gx || !gy) return SPHB_E_ARG;
+    *gx = (float)accel_y_raw / (1 << 14) * prm->g;      // :439
+    *gy = -(float)accel_x_raw / (1 << 14) * prm->g;     // :440
+    return SPHB_OK;
+}
+
+int sphb_create(const sphb_params *prm, sphb_ctx **out)
+{
+    if (!prm || !out) { set_error("null argument"); return SPHB_E_ARG; }
+    *out = nullptr;
+    if (!(prm->H > 0) || !(prm->cell_length > 0) || !(prm->x_max > prm->x_min) || !(prm->y_max > prm->y_min)) {
+        set_error("bad geometry (H=%g cell=%g)", prm->H, prm->cell_length);
+        return SPHB_E_ARG;
+    }
+    int rc = check_device(prm->device);
+    if (rc) return rc;
+    SPHB_CUDA(cudaSetDevice(prm->device));
+    const double rows = floor(((double)prm->y_max - prm->y_min) / prm->cell_length) + 1;
+    const double cols = floor(((double)prm->x_max - prm->x_min) / prm->cell_length) + 1;
+    if (rows * cols > 2.0e9) { set_error("grid of %.0f x %.0f cells exceeds 2^31", rows, cols); return SPHB_E_ARG; }
+
+    sphb_ctx *c = new (std::nothrow) sphb_ctx();
+    if (!c) return SPHB_E_NOMEM;
+    c->prm = *prm;
+    c->device = prm->device;
+    c->k = make_consts(*prm, prm->rho0 * prm->vol);
+    cudaDeviceProp prop;
+    SPHB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    c->sm_count = prop.multiProcessorCount;
+    SPHB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_counters), sizeof(DeviceCounters)));
+    SPHB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_gravity), sizeof(float2) * 4096));
+    c->scan.n_tiles = (c->k.ncells + kScanTile - 1) / kScanTile;
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->scan.tile_state), sizeof(unsigned long long) * (c->scan.n_tiles + 1)));
+    SPHB_CUDA(cudaMemset(c->scan.tile_state, 0, sizeof(unsigned long long) * (c->scan.n_tiles + 1)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->scan.tile_counter), sizeof(unsigned long long)));
+    SPHB_CUDA(cudaMemset(c->scan.tile_counter, 0, sizeof(unsigned long long)));
+    for (int i = 0; i < 128; i++) SPHB_CUDA(cudaEventCreate(&c->ev[i]));
+    *out = c;
+    return SPHB_OK;
+}
+
+int sphb_destroy(sphb_ctx *c)
+{
+    if (!c) return SPHB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_set(c->fluid);
+    free_set(c->boundary);
+    cudaFree(c->d_counters); cudaFree(c->d_gravity); cudaFree(c->d_stage);
+    cudaFree(c->d_pixels); cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_l2_scratch);
+    cudaFree(c->scan.tile_state); cudaFree(c->scan.tile_counter);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (int i = 0; i < 128; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return SPHB_OK;
+}
+
+int sphb_upload(sphb_ctx *c, const sphb_particle *fluid, int n_fluid, const sphb_particle *boundary, int n_boundary)
+{
+    SPHB_ENTER(c);
+    if (n_fluid < 0 || n_boundary < 0 || (n_fluid > 0 && !fluid) || (n_boundary > 0 && !boundary)) {
+        set_error("bad particle arrays"); return SPHB_E_ARG;
+    }
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    // uniform fluid mass (the reference sets every m = RHO_0*V, :502) selects the kernels
+    // that keep the mass in the constant bank
+    bool uniform = true;
+    for (int i = 1; i < n_fluid && uniform; i++) uniform = (memcmp(&fluid[i].m, &fluid[0].m, sizeof(float)) == 0);
+    int rc = alloc_set(c->fluid, n_fluid, c->k.ncells, false, !uniform);
+    if (rc) return rc;
+    c->fluid.uniform_mass = uniform;
+    c->fluid.uniform_mass_value = n_fluid > 0 ? fluid[0].m : c->prm.rho0 * c->prm.vol;
+    c->k.mass = c->fluid.uniform_mass_value;
+    const size_t fb = (size_t)n_fluid * sizeof(sphb_particle), bb = (size_t)n_boundary * sizeof(sphb_particle);
+    rc = ensure_stage(c, (fb > bb ? fb : bb) + 16);
+    if (rc) return rc;
+    if (n_fluid > 0) {
+        SPHB_CUDA(cudaMemcpyAsync(c->d_stage, fluid, fb, cudaMemcpyHostToDevice, c->stream));
+        c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(c->d_stage), c->fluid, false);
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));     // d_stage is reused below
+    }
+    if (n_boundary > 0) {
+        rc = alloc_set(c->boundary, n_boundary, c->k.ncells, true, true);
+        if (rc) return rc;
+        c->boundary.uniform_mass = false;
+        SPHB_CUDA(cudaMemcpyAsync(c->d_stage, boundary, bb, cudaMemcpyHostToDevice, c->stream));
+        c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(c->d_stage), c->boundary, true);
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        c->boundary.n = 0;
+        c->boundary.sorted = false;
+    }
+    c->boundary_ready = false;
+    c->accel_ready = false;
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+int sphb_init_boundary(sphb_ctx *c)
+{
+    SPHB_ENTER(c);
+    if (c->boundary.n > 0) {
+        build_grid(c, c->boundary, false);                                        // :600
+        ProfScope p(c, SPHB_K_OTHER);
+        c->launches += launch_pseudomass(c->stream, c->k, c->boundary);            // :601
+    }
+    c->boundary_ready = true;
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+int sphb_compute_accel(sphb_ctx *c, float gx, float gy)
+{
+    SPHB_ENTER(c);
+    if (c->fluid.n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
+    if (c->boundary.n > 0 && !c->boundary_ready) { set_error("sphb_init_boundary not called"); return SPHB_E_STATE; }
+    build_grid(c, c->fluid, false);                      // :604
+    density_force(c, gx, gy, nullptr, false);            // :605-607
+    c->accel_ready = true;
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int nsteps)
+{
+    SPHB_ENTER(c);
+    if (nsteps < 0) return SPHB_E_ARG;
+    if (c->fluid.n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
+    if (!c->accel_ready) { set_error("sphb_compute_accel must run before sphb_step (:604-607 precede :610)"); return SPHB_E_STATE; }
+    for (int s = 0; s < nsteps; s++) {
+        if (trace) { gx = trace[2 * s]; gy = trace[2 * s + 1]; }    // the value every thread reads at :632
+        build_grid(c, c->fluid, true);                   // :615-626
+        density_force(c, gx, gy, nullptr, true);         // :630-640
+        c->steps++;
+    }
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+int sphb_step(sphb_ctx *c, float gx, float gy, int nsteps) { return step_impl(c, gx, gy, nullptr, nsteps); }
+
+int sphb_step_trace(sphb_ctx *c, const float *gravity_xy, int nsteps)
+{
+    if (!gravity_xy && nsteps > 0) return SPHB_E_ARG;
+    return step_impl(c, 0.0f, 0.0f, gravity_xy, nsteps);
+}
+
+int sphb_synchronize(sphb_ctx *c)
+{
+    SPHB_ENTER(c);
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+int sphb_download(sphb_ctx *c, sphb_particle *fluid_out, float *du_dt, float *dv_dt)
+{
+    SPHB_ENTER(c);
+    const int n = c->fluid.n;
+    if (n <= 0) return SPHB_OK;
+    if ((du_dt == nullptr) != (dv_dt == nullptr)) { set_error("du_dt and dv_dt go together"); return SPHB_E_ARG; }
+    const size_t ab = (size_t)n * sizeof(sphb_particle), db = (size_t)n * sizeof(float);
+    int rc = ensure_stage(c, ab + 2 * db + 64);
+    if (rc) return rc;
+    char *base = static_cast<char *>(c->d_stage);
+    sphb_particle *d_aos = reinterpret_cast<sphb_particle *>(base);
+    float *d_du = reinterpret_cast<float *>(base + ((ab + 15) & ~(size_t)15));
+    float *d_dv = d_du + n;
+    c->launches += launch_soa_to_aos(c->stream, c->fluid, fluid_out ? d_aos : nullptr, du_dt ? d_du : nullptr,
+                                     du_dt ? d_dv : nullptr, false);
+    if (fluid_out) SPHB_CUDA(cudaMemcpyAsync(fluid_out, d_aos, ab, cudaMemcpyDeviceToHost, c->stream));
+    if (du_dt) {
+        SPHB_CUDA(cudaMemcpyAsync(du_dt, d_du, db, cudaMemcpyDeviceToHost, c->stream));
+        SPHB_CUDA(cudaMemcpyAsync(dv_dt, d_dv, db, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+int sphb_download_boundary(sphb_ctx *c, sphb_particle *boundary_out)
+{
+    SPHB_ENTER(c);
+    const int n = c->boundary.n;
+    if (n <= 0 || !boundary_out) return SPHB_OK;
+    const size_t ab = (size_t)n * sizeof(sphb_particle);
+    int rc = ensure_stage(c, ab + 64);
+    if (rc) return rc;
+    c->launches += launch_soa_to_aos(c->stream, c->boundary, reinterpret_cast<sphb_particle *>(c->d_stage), nullptr, nullptr, true);
+    SPHB_CUDA(cudaMemcpyAsync(boundary_out, c->d_stage, ab, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+int sphb_grid_shape(sphb_ctx *c, int *rows, int *cols)
+{
+    if (!c) return SPHB_E_ARG;
+    if (rows) *rows = c->k.rows;
+    if (cols) *cols = c->k.cols;
+    return SPHB_OK;
+}
+
+int sphb_cell_ids(sphb_ctx *c, int *cell_out)
+{
+    SPHB_ENTER(c);
+    const int n = c->fluid.n;
+    if (n <= 0 || !cell_out) return SPHB_E_ARG;
+    int rc = ensure_stage(c, (size_t)n * sizeof(int) + 64);
+    if (rc) return rc;
+    c->launches += launch_cell_ids(c->stream, c->k, c->fluid, static_cast<int *>(c->d_stage));
+    SPHB_CUDA(cudaMemcpyAsync(cell_out, c->d_stage, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    return SPHB_OK;
+}
+
+int sphb_neighbor_lists(sphb_ctx *c, int which, int cap, int *counts, int *lists)
+{
+    SPHB_ENTER(c);
+    if (which < 0 || which > 2 || cap <= 0 || !counts || !lists) return SPHB_E_ARG;
+    const ParticleSet &a = which == 2 ? c->boundary : c->fluid;
+    const ParticleSet &b = which == 0 ? c->fluid : c->boundary;
+    if (a.n <= 0) return SPHB_E_STATE;
+    if (!b.sorted || (which == 0 && !a.sorted)) { set_error("grid not built yet"); return SPHB_E_STATE; }
+    const size_t cb = (size_t)a.n * sizeof(int), lb = (size_t)a.n * cap * sizeof(int);
+    int rc = ensure_stage(c, cb + lb + 64);
+    if (rc) return rc;
+    int *d_counts = static_cast<int *>(c->d_stage);
+    int *d_lists = d_counts + (((size_t)a.n + 3) & ~(size_t)3);
+    unsigned int *d_over = &c->d_counters->list_flushes;   // borrowed as a scratch counter
+    SPHB_CUDA(cudaMemsetAsync(d_over, 0, sizeof(unsigned int), c->stream));
+    SPHB_CUDA(cudaMemsetAsync(d_lists, 0xff, lb, c->stream));
+    c->launches += launch_neighbor_lists(c->stream, c->k, a, b, which != 1, cap, d_counts, d_lists, d_over);
+    unsigned int over = 0;
+    SPHB_CUDA(cudaMemcpyAsync(counts, d_counts, cb, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaMemcpyAsync(lists, d_lists, lb, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaMemcpyAsync(&over, d_over, sizeof over, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaMemsetAsync(d_over, 0, sizeof(unsigned int), c->stream));
+    return (int)over;
+}
+
+int sphb_pair_stats(sphb_ctx *c, double *cand, double *acc)
+{
+    SPHB_ENTER(c);
+    if (c->fluid.n <= 0 || !c->fluid.sorted) return SPHB_E_STATE;
+    DeviceCounters h;
+    SPHB_CUDA(cudaMemsetAsync(&c->d_counters->pair_candidates, 0, 2 * sizeof(unsigned long long), c->stream));
+    // a counting density pass writes the same rho/p it would anyway
+    c->launches += launch_density(c->stream, c->k, c->fluid, c->boundary, c->d_counters, true);
+    SPHB_CUDA(cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    if (cand) *cand = (double)h.pair_candidates / c->fluid.n;
+    if (acc) *acc = (double)h.pair_accepted / c->fluid.n;
+    return SPHB_OK;
+}
+
+int sphb_profile(sphb_ctx *c, int mode)
+{
+    SPHB_ENTER(c);
+    int rc = prof_drain(c);
+    c->profile_mode = mode;
+    return rc;
+}
+
+int sphb_profile_read(sphb_ctx *c, double ms[SPHB_K_COUNT], unsigned long long launches[SPHB_K_COUNT], int reset)
+{
+    SPHB_ENTER(c);
+    int rc = prof_drain(c);
+    if (rc) return rc;
+    for (int i = 0; i < SPHB_K_COUNT; i++) {
+        if (ms) ms[i] = c->prof_ms[i];
+        if (launches) launches[i] = c->prof_launches[i];
+        if (reset) { c->prof_ms[i] = 0; c->prof_launches[i] = 0; }
+    }
+    return SPHB_OK;
+}
+
+int sphb_render(sphb_ctx *c, unsigned char *draw_buffer)
+{
+    SPHB_ENTER(c);
+    if (!draw_buffer) return SPHB_E_ARG;
+    if (c->fluid.n <= 0 || !c->fluid.sorted) { set_error("no sorted fluid state to render"); return SPHB_E_STATE; }
+    if (!c->d_pixels) {
+        // pixel-centre pseudo-particles, :570-577 (double expression, rounded to float)
+        float2 *h = static_cast<float2 *>(malloc(sizeof(float2) * 64 * 128));
+        if (!h) return SPHB_E_NOMEM;
+        for (int i = 0; i < 64; i++)
+            for (int j = 0; j < 128; j++) {
+                h[i * 128 + j].x = (float)((j + 0.5) * (double)c->prm.width / 128);
+                h[i * 128 + j].y = (float)((64 - (i + 0.5)) * (double)c->prm.height / 64);
+            }
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&c->d_pixels), sizeof(float2) * 64 * 128);
+        if (e == cudaSuccess) e = cudaMemcpy(c->d_pixels, h, sizeof(float2) * 64 * 128, cudaMemcpyHostToDevice);
+        free(h);
+        SPHB_CUDA(e);
+        SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_frame), 1024));
+    }
+    const float px_width = c->prm.width / 128;                 // :399
+    const float W_px = host_W(c->prm.H, px_width / 2);          // :401
+    c->launches += launch_render(c->stream, c->k, c->fluid, c->d_pixels, W_px, c->d_frame);
+    SPHB_CUDA(cudaMemcpyAsync(draw_buffer, c->d_frame, 1024, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+static float key_to_float(unsigned int key)
+{
+    const unsigned int u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    float f;
+    memcpy(&f, &u, sizeof f);
+    return f;
+}
+
+int sphb_get_stats(sphb_ctx *c, sphb_stats *out)
+{
+    SPHB_ENTER(c);
+    if (!out) return SPHB_E_ARG;
+    memset(out, 0, sizeof *out);
+    if (!c->d_stats) SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), 64));
+    struct { double d[4]; unsigned int u[4]; } h;
+    memset(&h, 0, sizeof h);
+    DeviceCounters ctr;
+    memset(&ctr, 0, sizeof ctr);
+    if (c->fluid.n > 0) {
+        SPHB_CUDA(cudaMemsetAsync(c->d_stats, 0, 64, c->stream));
+        c->launches += launch_stats(c->stream, c->k, c->fluid, c->d_stats, reinterpret_cast<float *>(c->d_stats + 4));
+        SPHB_CUDA(cudaMemcpyAsync(&h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SPHB_CUDA(cudaMemcpyAsync(&ctr, c->d_counters, sizeof ctr, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    out->mass = h.d[0]; out->mom_x = h.d[1]; out->mom_y = h.d[2]; out->kinetic = h.d[3];
+    memcpy(&out->max_speed, &h.u[0], sizeof(float));
+    if (c->fluid.n > 0) {
+        out->max_rho = key_to_float(h.u[1]);
+        out->min_rho = key_to_float(~h.u[2]);
+        out->max_rho_err = out->max_rho - c->prm.rho0;
+        float last;
+        memcpy(&last, &h.u[3], sizeof last);
+        out->last_rho_err_ref = last - c->prm.rho0;      // :657-659 as written
+    }
+    out->n_escaped = ctr.n_escaped;
+    out->max_cell_count = ctr.max_cell_count;
+    out->n_fluid = (unsigned int)c->fluid.n;
+    out->n_boundary = (unsigned int)c->boundary.n;
+    out->steps = c->steps;
+    return SPHB_OK;
+}
+
+int sphb_flush_l2(sphb_ctx *c)
+{
+    SPHB_ENTER(c);
+    const size_t bytes = (size_t)256 << 20;
+    if (!c->d_l2_scratch) SPHB_CUDA(cudaMalloc(&c->d_l2_scratch, bytes));
+    c->l2_flush_value ^= 0x5a;
+    SPHB_CUDA(cudaMemsetAsync(c->d_l2_scratch, c->l2_flush_value, bytes, c->stream));
+    return SPHB_OK;
+}
+
+void *sphb_stream(sphb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+unsigned long long sphb_launch_count(sphb_ctx *c) { return c ? c->launches : 0ULL; }
+
+}  // extern "C"

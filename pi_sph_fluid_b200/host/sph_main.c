@@ -1,0 +1,164 @@
+/* sph_main.c — plain-C host driver over the C ABI of libsphb200.so.
+ *
+ * Mirrors the structure of the reference's main() (pi_sph_fluid.c:475-704): build the scene
+ * (:484-540), print dt / particle counts (:543-545), initialise the boundary pseudo-mass and
+ * the zero-th accelerations (:600-607), then loop { step; draw at 60 Hz; statistics every
+ * 0.1 s of simulated time } (:610-691).  What differs: the state lives in HBM behind
+ * sphb_ctx, the OLED is replaced by an optional ASCII dump of the same 1 KiB SSD1306 frame,
+ * the MPU6050 by an optional synthetic tilt trace, and the run is bounded (--steps).
+ *
+ *   sph_b200_main [--scene drop|dam|tank] [--R 0.075] [--steps 4000] [--chunk 50]
+ *                 [--tilt DEG] [--render] [--nondeterministic] [--device 0]
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "sph_b200.h"
+#include "sph_b200_scene.h"
+
+static double now_s(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+#define CHECK(call)                                                                  \
+    do {                                                                             \
+        int rc__ = (call);                                                           \
+        if (rc__ < 0) {                                                              \
+            fprintf(stderr, "%s failed (%d): %s\n", #call, rc__, sphb_last_error()); \
+            return 1;                                                                \
+        }                                                                            \
+    } while (0)
+
+/* the SSD1306 page layout of :407-408: byte (i/8)*128+j, bit i%8 */
+static void print_frame(const unsigned char *buf)
+{
+    for (int i = 0; i < 64; i += 2) {
+        char line[129];
+        for (int j = 0; j < 128; j++) {
+            int top = (buf[i / 8 * 128 + j] >> (i % 8)) & 1;
+            int bot = (buf[(i + 1) / 8 * 128 + j] >> ((i + 1) % 8)) & 1;
+            line[j] = top && bot ? '#' : (top ? '"' : (bot ? '_' : ' '));
+        }
+        line[128] = 0;
+        puts(line);
+    }
+}
+
+int main(int argc, char **argv)
+{
+    const char *scene = "drop";
+    float R = 0.0750f;                /* :11 */
+    const float WIDTH = 4.0f, HEIGHT = 2.0f;   /* :13-14 */
+    long steps = 4000;
+    int chunk = 50, render = 0, deterministic = 1, device = 0;
+    float tilt_deg = 0.0f;
+    for (int i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "--scene") && i + 1 < argc) scene = argv[++i];
+        else if (!strcmp(argv[i], "--R") && i + 1 < argc) R = (float)atof(argv[++i]);
+        else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atol(argv[++i]);
+        else if (!strcmp(argv[i], "--chunk") && i + 1 < argc) chunk = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--tilt") && i + 1 < argc) tilt_deg = (float)atof(argv[++i]);
+        else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--render")) render = 1;
+        else if (!strcmp(argv[i], "--nondeterministic")) deterministic = 0;
+        else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
+    }
+    if (chunk < 1) chunk = 1;
+
+    sphb_params prm;
+    CHECK(sphb_default_params(&prm, R, WIDTH, HEIGHT));
+    prm.deterministic = deterministic;
+    prm.device = device;
+
+    /* scene, :484-540 */
+    int n_fluid, n_boundary;
+    sphb_particle *fluid, *boundary;
+    if (!strcmp(scene, "drop")) {
+        n_fluid = sphb_scene_count_drop(&prm);
+        fluid = (sphb_particle *)malloc(sizeof *fluid * (size_t)(n_fluid > 0 ? n_fluid : 1));
+        sphb_scene_fill_drop(&prm, fluid);
+    } else {
+        /* dam: column x in [R,2), y in [R,1);  tank: filled to y = 1 across the width */
+        const float x1 = !strcmp(scene, "dam") ? 2.0f : WIDTH - 0.5f * R;
+        n_fluid = sphb_scene_count_block(&prm, R, x1, R, 1.0f);
+        fluid = (sphb_particle *)malloc(sizeof *fluid * (size_t)(n_fluid > 0 ? n_fluid : 1));
+        sphb_scene_fill_block(&prm, R, x1, R, 1.0f, fluid);
+    }
+    n_boundary = sphb_scene_count_boundary(&prm);
+    boundary = (sphb_particle *)malloc(sizeof *boundary * (size_t)n_boundary);
+    sphb_scene_fill_boundary(&prm, boundary);
+    float *du_dt = (float *)malloc(sizeof(float) * (size_t)n_fluid);
+    float *dv_dt = (float *)malloc(sizeof(float) * (size_t)n_fluid);
+
+    printf("dt = %f    (expected ticks/s) %d\n", prm.dt, (int)(1 / prm.dt));     /* :543 */
+    printf("n_fluid = %d\n", n_fluid);                                            /* :544 */
+    printf("n_boundary = %d\n", n_boundary);                                      /* :545 */
+
+    sphb_ctx *ctx = NULL;
+    CHECK(sphb_create(&prm, &ctx));
+    CHECK(sphb_upload(ctx, fluid, n_fluid, boundary, n_boundary));
+    CHECK(sphb_init_boundary(ctx));                                               /* :600-601 */
+    float gx = 0.0f, gy = -prm.g;                                                 /* :442-443 */
+    CHECK(sphb_compute_accel(ctx, gx, gy));                                       /* :604-607 */
+
+    float *trace = NULL;
+    if (tilt_deg != 0.0f) {
+        trace = (float *)malloc(sizeof(float) * 2 * (size_t)chunk);
+    }
+    unsigned char frame[1024];
+    memset(frame, 0, sizeof frame);                                               /* :563 */
+    float worst_max_rho_error_pct = 0, max_max_speed = 0;                         /* :583 */
+    double t = 0, last_t = 0;
+    double last_reported = now_s(), last_drew = last_reported, t_begin = last_reported;
+
+    for (long done = 0; done < steps;) {
+        const int n = (int)((steps - done) < chunk ? (steps - done) : chunk);
+        if (trace) {
+            /* one sample per 410 steps ~ the reference's 10 Hz poll at dt = 2.44e-4 (:454-463) */
+            float *full = (float *)malloc(sizeof(float) * 2 * (size_t)(done + n));
+            sphb_gravity_trace_tilt(&prm, tilt_deg, 4 * 4102, 410, (int)(done + n), full);
+            memcpy(trace, full + 2 * done, sizeof(float) * 2 * (size_t)n);
+            free(full);
+            CHECK(sphb_step_trace(ctx, trace, n));
+        } else {
+            CHECK(sphb_step(ctx, gx, gy, n));                                     /* :612-641 */
+        }
+        done += n;
+        t += (double)n * prm.dt;                                                  /* :678 */
+
+        const double now = now_s();
+        if (render && now - last_drew > 1.0 / 60) {                               /* :648 */
+            CHECK(sphb_render(ctx, frame));                                       /* :649 */
+            print_frame(frame);
+            last_drew = now;
+        }
+        if (t - last_t > 0.1 || done == steps) {                                  /* :679 */
+            sphb_stats st;
+            CHECK(sphb_get_stats(ctx, &st));
+            const double wall = now_s() - last_reported;
+            const float max_rho_error_pct = st.max_rho_err / prm.rho0 * 100;      /* :660, bug fixed */
+            if (max_rho_error_pct > worst_max_rho_error_pct) worst_max_rho_error_pct = max_rho_error_pct;
+            if (st.max_speed > max_max_speed) max_max_speed = st.max_speed;
+            printf("sim time: %.2f, ticks/s: %d, max rho error: %.3f%% (worst) %.3f%%, "
+                   "max speed: %.1f m/s (worst) %.1f m/s, escaped: %u\n",
+                   t, (int)(((t - last_t) / prm.dt) / wall), max_rho_error_pct, worst_max_rho_error_pct,
+                   st.max_speed, max_max_speed, st.n_escaped);                    /* :683-687 */
+            last_t = t;
+            last_reported = now_s();
+        }
+    }
+    CHECK(sphb_download(ctx, fluid, du_dt, dv_dt));
+    const double wall = now_s() - t_begin;
+    printf("%ld steps of %d particles in %.3f s: %.3e particle-updates/s\n", steps, n_fluid, wall,
+           (double)steps * n_fluid / wall);
+    if (render) { CHECK(sphb_render(ctx, frame)); print_frame(frame); }
+    sphb_destroy(ctx);
+    free(fluid); free(boundary); free(du_dt); free(dv_dt); free(trace);
+    return 0;
+}
