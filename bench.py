@@ -113,7 +113,7 @@ def build_scene(pkg, spec, deterministic=True, device=0):
         fluid = pkg.scene_drop(prm)
     else:
         x1, y1 = spec["block"]
-        fluid = pkg.scene_block(prm, spec["R"], x1, spec["R"], y1)
+        fluid = pkg.scene_block(prm, 2 * spec["R"], x1, 2 * spec["R"], y1)     # 2R off the walls (DESIGN.md "Scenes")
     boundary = pkg.scene_boundary(prm)
     return prm, fluid, boundary
 

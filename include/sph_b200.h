@@ -104,6 +104,10 @@ int sphb_init_boundary(sphb_ctx *ctx);
  * calculate_particle_pressure + calculate_accelerations on the state as it is */
 int sphb_compute_accel(sphb_ctx *ctx, float gravity_x, float gravity_y);
 
+/* Restores the caller-owned du_dt/dv_dt arrays (:492-493) of a saved state (original order),
+ * so a run can continue from a checkpoint exactly where :612 would: the next kick uses them. */
+int sphb_upload_accel(sphb_ctx *ctx, const float *du_dt, const float *dv_dt);
+
 /* :612-641  nsteps iterations of the leapfrog body (kick, drift, grid rebuild, density,
  * pressure, accelerations, kick) with constant gravity.  Asynchronous on the handle's
  * stream; sphb_download / sphb_stats / sphb_synchronize wait for it. */

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         "sphb_upload": (ci, [vp, vp, ci, vp, ci]),
         "sphb_init_boundary": (ci, [vp]),
         "sphb_compute_accel": (ci, [vp, cf, cf]),
+        "sphb_upload_accel": (ci, [vp, vp, vp]),
         "sphb_step": (ci, [vp, cf, cf, ci]),
         "sphb_step_trace": (ci, [vp, vp, ci]),
         "sphb_download": (ci, [vp, vp, vp, vp]),
@@ -226,6 +227,11 @@ class Simulation:
 
     def compute_accel(self, gx: float = 0.0, gy: float = -9.81):   # :604-607
         _check(lib().sphb_compute_accel(self._h, gx, gy), "sphb_compute_accel")
+
+    def upload_accel(self, du: np.ndarray, dv: np.ndarray):        # :492-493 restored from a checkpoint
+        du = np.ascontiguousarray(du, np.float32); dv = np.ascontiguousarray(dv, np.float32)
+        assert len(du) == len(dv) == self.n_fluid
+        _check(lib().sphb_upload_accel(self._h, _p(du), _p(dv)), "sphb_upload_accel")
 
     def step(self, nsteps: int = 1, gx: float = 0.0, gy: float = -9.81):   # :612-641
         _check(lib().sphb_step(self._h, gx, gy, nsteps), "sphb_step")

@@ -217,7 +217,8 @@ k_reorder(const int n, const uint32_t *__restrict__ key, const uint32_t *__restr
           const float2 *__restrict__ pos_in, const float2 *__restrict__ vel_in,
           const uint32_t *__restrict__ id_in, const float *__restrict__ mass_in,
           const float *__restrict__ aux_in, float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
-          uint32_t *__restrict__ id_out, float *__restrict__ mass_out, float *__restrict__ aux_out)
+          uint32_t *__restrict__ id_out, float *__restrict__ mass_out, float *__restrict__ aux_out,
+          uint32_t *__restrict__ cellkey_out, const int cols)
 {
     const int s = blockIdx.x * kStreamThreads + threadIdx.x;
     if (s >= n) return;
@@ -238,13 +239,13 @@ k_reorder(const int n, const uint32_t *__restrict__ key, const uint32_t *__restr
     pos_out[dst] = pos_in[s];
     vel_out[dst] = vel_in[s];
     id_out[dst] = my;
+    cellkey_out[dst] = ((c / (uint32_t)cols) << 16) | (c % (uint32_t)cols);     // row | col, < 65536 each
     if (MASS) mass_out[dst] = mass_in[s];
     if (AUX) aux_out[dst] = aux_in[s];
 }
 
 int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deterministic)
 {
-    (void)k;
     if (ps.n == 0) return 0;
     const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
     int launches = 0;
@@ -261,7 +262,7 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
 #define SPHB_REORDER(D, M, A)                                                                           \
     k_reorder<D, M, A><<<grid, kStreamThreads, 0, st>>>(ps.n, ps.key, ps.rank, ps.cell_start, ps.ids_tmp, \
         ps.pos[ps.pc], ps.vel[ps.vc], ps.id[ps.ic], mass_in, aux_in, ps.pos[ps.pc ^ 1],                  \
-        ps.vel[ps.vc ^ 1], ps.id[ps.ic ^ 1], mass_out, aux_out)
+        ps.vel[ps.vc ^ 1], ps.id[ps.ic ^ 1], mass_out, aux_out, ps.cellkey, k.cols)
     if (deterministic) {
         if (has_mass && has_aux) SPHB_REORDER(true, true, true);
         else if (has_mass) SPHB_REORDER(true, true, false);
@@ -347,6 +348,24 @@ int launch_soa_to_aos(cudaStream_t st, const ParticleSet &ps, sphb_particle *aos
         ps.uniform_mass_value, is_boundary ? ps.aux[ps.xc] : nullptr, is_boundary ? nullptr : ps.rho_prr,
         is_boundary ? nullptr : ps.p, ps.acc, reinterpret_cast<float *>(aos), is_boundary ? nullptr : du,
         is_boundary ? nullptr : dv);
+    return 1;
+}
+
+// du_dt/dv_dt in original order -> acc[] in the set's current order
+__global__ void __launch_bounds__(kStreamThreads)
+k_set_accel(const int n, const uint32_t *__restrict__ id, const float *__restrict__ du,
+            const float *__restrict__ dv, float2 *__restrict__ acc)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t i = id[s];
+    acc[s] = make_float2(du[i], dv[i]);
+}
+
+int launch_set_accel(cudaStream_t st, ParticleSet &ps, const float *du, const float *dv)
+{
+    if (ps.n == 0) return 0;
+    k_set_accel<<<(ps.n + kStreamThreads - 1) / kStreamThreads, kStreamThreads, 0, st>>>(ps.n, ps.id[ps.ic], du, dv, ps.acc);
     return 1;
 }
 

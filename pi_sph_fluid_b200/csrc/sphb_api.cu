@@ -36,7 +36,7 @@ static void free_set(ParticleSet &ps)
         cudaFree(ps.pos[i]); cudaFree(ps.vel[i]); cudaFree(ps.id[i]); cudaFree(ps.mass[i]); cudaFree(ps.aux[i]);
     }
     cudaFree(ps.acc); cudaFree(ps.rho_prr); cudaFree(ps.p); cudaFree(ps.key); cudaFree(ps.rank);
-    cudaFree(ps.ids_tmp); cudaFree(ps.cell_count); cudaFree(ps.cell_start);
+    cudaFree(ps.ids_tmp); cudaFree(ps.cell_count); cudaFree(ps.cell_start); cudaFree(ps.cellkey);
     ps = ParticleSet();
 }
 
@@ -75,10 +75,14 @@ int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_ma
     SPHB_CUDA(dmalloc(&ps.key, m));
     SPHB_CUDA(dmalloc(&ps.rank, m));
     SPHB_CUDA(dmalloc(&ps.ids_tmp, m));
+    SPHB_CUDA(dmalloc(&ps.cellkey, m));
     SPHB_CUDA(dmalloc(&ps.cell_count, (size_t)ncells + 8));
     SPHB_CUDA(dmalloc(&ps.cell_start, (size_t)ncells + 8));
     SPHB_CUDA(cudaMemset(ps.cell_count, 0, ((size_t)ncells + 8) * sizeof(uint32_t)));
     SPHB_CUDA(cudaMemset(ps.cell_start, 0, ((size_t)ncells + 8) * sizeof(uint32_t)));
+    // the memsets above ran on the legacy default stream, which does not order against the
+    // handle's non-blocking stream
+    SPHB_CUDA(cudaDeviceSynchronize());
     ps.n = n;
     ps.cap = n;
     return SPHB_OK;
@@ -181,7 +185,7 @@ const char *sphb_last_error(void) { return g_err; }
 
 const char *sphb_build_info(void)
 {
-    return "libsphb200 v1: sm_100a, nvcc " __DATE__ ", pair CTA 128 thr, tile 768, list 64";
+    return "libsphb200 v1: sm_100a, nvcc " __DATE__ ", pair CTA 128 thr, tile 576, list 48";
 }
 
 int sphb_default_params(sphb_params *prm, float R, float width, float height)
@@ -226,6 +230,7 @@ int sphb_create(const sphb_params *prm, sphb_ctx **out)
     const double rows = floor(((double)prm->y_max - prm->y_min) / prm->cell_length) + 1;
     const double cols = floor(((double)prm->x_max - prm->x_min) / prm->cell_length) + 1;
     if (rows * cols > 2.0e9) { set_error("grid of %.0f x %.0f cells exceeds 2^31", rows, cols); return SPHB_E_ARG; }
+    if (rows >= 65536.0 || cols >= 65536.0) { set_error("grid of %.0f x %.0f cells: a dimension exceeds 65535", rows, cols); return SPHB_E_ARG; }
 
     sphb_ctx *c = new (std::nothrow) sphb_ctx();
     if (!c) return SPHB_E_NOMEM;
@@ -245,6 +250,7 @@ int sphb_create(const sphb_params *prm, sphb_ctx **out)
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->scan.tile_counter), sizeof(unsigned long long)));
     SPHB_CUDA(cudaMemset(c->scan.tile_counter, 0, sizeof(unsigned long long)));
     for (int i = 0; i < 128; i++) SPHB_CUDA(cudaEventCreate(&c->ev[i]));
+    SPHB_CUDA(cudaDeviceSynchronize());      // memsets above vs. the non-blocking stream
     *out = c;
     return SPHB_OK;
 }
@@ -329,6 +335,26 @@ int sphb_compute_accel(sphb_ctx *c, float gx, float gy)
     density_force(c, gx, gy, nullptr, false);            // :605-607
     c->accel_ready = true;
     SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+int sphb_upload_accel(sphb_ctx *c, const float *du_dt, const float *dv_dt)
+{
+    SPHB_ENTER(c);
+    const int n = c->fluid.n;
+    if (n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
+    if (!du_dt || !dv_dt) return SPHB_E_ARG;
+    const size_t db = (size_t)n * sizeof(float);
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    int rc = ensure_stage(c, 2 * db + 64);
+    if (rc) return rc;
+    float *d_du = static_cast<float *>(c->d_stage), *d_dv = d_du + n;
+    SPHB_CUDA(cudaMemcpyAsync(d_du, du_dt, db, cudaMemcpyHostToDevice, c->stream));
+    SPHB_CUDA(cudaMemcpyAsync(d_dv, dv_dt, db, cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_set_accel(c->stream, c->fluid, d_du, d_dv);
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    c->accel_ready = true;
     return SPHB_OK;
 }
 

@@ -12,8 +12,9 @@ namespace sphb {
 // ---- tunables ----------------------------------------------------------------------------
 constexpr int kStreamThreads = 256;   // advect/bin, reorder, gather/scatter kernels
 constexpr int kPairThreads = 128;     // density / force CTAs: one thread per particle
-constexpr int kListCap = 64;          // per-thread accepted-neighbour list (u16, staged mode)
-constexpr int kTileCap = 768;         // staged neighbourhood entries per CTA
+constexpr int kListCap = 48;          // per-thread accepted list entries (u16 tile offsets) before a flush
+constexpr int kDensityListCap = 40;   // same for the density pass's list of f32 squared distances
+constexpr int kTileCap = 576;         // staged neighbourhood entries per CTA (x 8 B must stay < 64 KiB)
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -34,6 +35,7 @@ struct ParticleSet {
     float *aux[2] = {nullptr, nullptr};       // boundary: the rho field handed in (:526-538)
     float uniform_mass_value = 0.0f;
     uint32_t *key = nullptr, *rank = nullptr; // counting-sort scratch
+    uint32_t *cellkey = nullptr;              // (row << 16 | col) of the particle in each sorted slot
     uint32_t *ids_tmp = nullptr;              // deterministic-rank scratch
     uint32_t *cell_count = nullptr;           // ncells, zero between builds
     uint32_t *cell_start = nullptr;           // ncells + 1
@@ -110,6 +112,7 @@ int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc
 int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deterministic);
 int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, bool is_boundary);
 int launch_soa_to_aos(cudaStream_t st, const ParticleSet &ps, sphb_particle *aos, float *du, float *dv, bool is_boundary);
+int launch_set_accel(cudaStream_t st, ParticleSet &ps, const float *du, const float *dv);
 int launch_cell_ids(cudaStream_t st, const Consts &k, const ParticleSet &ps, int *cell_out);
 
 // ---- kernel launchers (kernels_pair.cu) ----------------------------------------------------

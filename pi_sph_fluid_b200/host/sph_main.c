@@ -84,11 +84,13 @@ int main(int argc, char **argv)
         fluid = (sphb_particle *)malloc(sizeof *fluid * (size_t)(n_fluid > 0 ? n_fluid : 1));
         sphb_scene_fill_drop(&prm, fluid);
     } else {
-        /* dam: column x in [R,2), y in [R,1);  tank: filled to y = 1 across the width */
-        const float x1 = !strcmp(scene, "dam") ? 2.0f : WIDTH - 0.5f * R;
-        n_fluid = sphb_scene_count_block(&prm, R, x1, R, 1.0f);
+        /* dam: column x in [2R,2), y in [2R,1);  tank: filled to y = 1 across the width.  The
+         * blocks start 2R off the walls: one lattice step away the Akinci single-layer wall
+         * (psi ~ 4.2 m) would put rho at 1700 and p at 9e8 Pa at t = 0. */
+        const float x1 = !strcmp(scene, "dam") ? 2.0f : WIDTH - 1.5f * R;
+        n_fluid = sphb_scene_count_block(&prm, 2 * R, x1, 2 * R, 1.0f);
         fluid = (sphb_particle *)malloc(sizeof *fluid * (size_t)(n_fluid > 0 ? n_fluid : 1));
-        sphb_scene_fill_block(&prm, R, x1, R, 1.0f, fluid);
+        sphb_scene_fill_block(&prm, 2 * R, x1, 2 * R, 1.0f, fluid);
     }
     n_boundary = sphb_scene_count_boundary(&prm);
     boundary = (sphb_particle *)malloc(sizeof *boundary * (size_t)n_boundary);

@@ -15,7 +15,8 @@ oracle_scene_* and cross-checked here against the counts the reference prints
 Files
   drop_R0.075.npz   config 1 (default scene): t=0 and after 1 / 100 / 2000 steps
                     (2000 is post-impact: p up to ~1.8e5 Pa), neighbour lists in the
-                    reference's visiting order at t=0 and step 2000, and the 1-bpp
+                    reference's visiting order at t=0 and step 2000 (plus acc_du/acc_dv: the reference's
+                    calculate_accelerations re-run on the stored snapshot), and the 1-bpp
                     metaball frame at step 2000.
   drop_R0.02.npz    the same scene at R = 0.02 (N = 3848, sed-widened reference
                     variant): state after 5000 steps (post-impact) and one step later —
@@ -62,6 +63,11 @@ def run(R_tag, R, snaps, with_lists, with_frame):
         out[f"du_{s}"] = du.copy()
         out[f"dv_{s}"] = dv.copy()
         if s in with_lists:
+            # calculate_accelerations of the reference on the snapshot AS STORED (velocities after
+            # the closing kick, :637-640) — du_/dv_ above were computed before that kick
+            f2 = fluid.copy()
+            out[f"acc_du_{s}"], out[f"acc_dv_{s}"] = ref.compute_accel(f2, boundary, cf, cb, *G)
+            assert all(np.array_equal(f2[k].view("u4"), fluid[k].view("u4")) for k in ("rho", "p"))
             out[f"ff_list_{s}"], out[f"ff_off_{s}"] = lists(ref, fluid, fluid, cf)
             out[f"fb_list_{s}"], out[f"fb_off_{s}"] = lists(ref, fluid, boundary, cb)
         if s in with_frame:

@@ -128,7 +128,7 @@ def test_operator_tier_against_reference_golden(lib_built, golden02, golden075):
         fluid["p"] = ref["p"]
         du, dv = np.zeros(len(fluid), np.float32), np.zeros(len(fluid), np.float32)
         c.calculate_accelerations(du, dv, fluid, g["boundary"].copy(), ctx_f, ctx_b, *G)           # :607
-        assert accel_err(du, dv, g[f"du_{snap}"], g[f"dv_{snap}"]).max() < TOL_A
+        assert accel_err(du, dv, g[f"acc_du_{snap}"], g[f"acc_dv_{snap}"]).max() < TOL_A
         for fld in FIELDS:
             assert same_bits(fluid[fld], ref[fld])                        # fluid untouched (:370-371)
 
@@ -187,25 +187,29 @@ def test_multi_step_against_oracle(oracle_built, lib_built, golden075):
 
 def test_one_step_from_post_impact_state(oracle_built, lib_built, golden02):
     """One full leapfrog step (kick, drift, rebuild, density, pressure, accel, kick) from the
-    reference's step-5000 state, against the chain oracle and the reference's step 5001."""
+    reference's step-5000 checkpoint (state + its du_dt/dv_dt arrays), against the reference's own
+    step 5001 and against the chain oracle."""
     g = golden02
     fluid = g["fluid_5000"]
-    # resident tier needs the accelerations of the uploaded state first (:604-607)
     sim = run_gpu(lib_built, 0.02, fluid, g["boundary_init"])
-    sim.compute_accel(*G)
+    sim.upload_accel(g["du_5000"], g["dv_5000"])           # the caller-owned arrays of :492-493
     sim.step(1, *G)
     f, du, dv = sim.download()
+    ref = g["fluid_5001"]
+    assert np.abs(f["x"] - ref["x"]).max() < 5e-7 and np.abs(f["y"] - ref["y"]).max() < 5e-7   # <= 2 ulp at x ~ 4
+    assert (np.abs(f["rho"].astype("f8") - ref["rho"]) / ref["rho"]).max() < TOL_RHO
+    assert p_ok(f["p"], ref["p"])
 
     o = oracle_built.Oracle(R=0.02, variant="chain")
     of, ob = fluid.copy(), g["boundary_init"].copy()
     gb = o.init_boundary(ob); gf = o.grid(len(of))
-    odu, odv = o.compute_accel(of, ob, gf, gb, *G)
+    odu, odv = g["du_5000"].copy(), g["dv_5000"].copy()
     o.step(of, ob, gf, gb, odu, odv, 1, *G)
-    assert np.abs(f["x"] - of["x"]).max() < 5e-7 and np.abs(f["y"] - of["y"]).max() < 5e-7     # <= 2 ulp at x ~ 4
-    assert (np.abs(f["rho"].astype("f8") - of["rho"]) / of["rho"]).max() < TOL_RHO
-    ref = g["fluid_5001"]
-    assert (np.abs(f["rho"].astype("f8") - ref["rho"]) / ref["rho"]).max() < TOL_RHO
-    assert np.abs(f["x"] - ref["x"]).max() < 5e-7
+    for fld in ("x", "y"):
+        assert same_bits(f[fld], of[fld]), fld             # kick1 + drift are exact
+    assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])
+    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    assert max(np.abs(f["u"] - of["u"]).max(), np.abs(f["v"] - of["v"]).max()) < 1e-4 * 0.5 * float(o.dt) * 4e3 + 1e-6
     assert np.array_equal(sim.cell_ids(), o.cell_ids(gf, of))
     sim.close()
 
@@ -395,7 +399,9 @@ def test_full_size_config2_properties(oracle_built, lib_built):
     # oracle after the same 50 steps (free fall, p == 0): positions agree to round-off
     o.step(of, ob, gf, gb, odu, odv, 50, *G)
     assert np.abs(f2["x"] - of["x"]).max() < 1e-6 and np.abs(f2["y"] - of["y"]).max() < 1e-6
-    assert (np.abs(f2["rho"].astype("f8") - of["rho"]) / of["rho"]).max() < TOL_RHO
+    # after 50 steps positions differ by <= 2 ulp (2.4e-7 m at x ~ 2-4 m) = 1.5e-4 H at this
+    # spacing, which moves rho by ~4e-6: the north-star tolerance, not the one-pass one, applies
+    assert (np.abs(f2["rho"].astype("f8") - of["rho"]) / of["rho"]).max() < 1e-4
     # run-to-run reproducibility of the deterministic mode
     sim2 = lib_built.Simulation(prm)
     sim2.upload(fluid, boundary); sim2.init_boundary(); sim2.compute_accel(*G); sim2.step(50, *G)
@@ -405,11 +411,13 @@ def test_full_size_config2_properties(oracle_built, lib_built):
 
 
 def test_dam_break_scene_steps(oracle_built, lib_built):
-    """Builder-defined dam break (SURVEY.md §8d cfg3 geometry, reduced R): 200 steps against the
-    chain oracle — integrals within the stated drift, nothing escapes."""
+    """Builder-defined dam break (SURVEY.md §8d cfg3 geometry, reduced R; the block starts 2R off
+    the walls — at R the single-layer wall, psi = 4.2 m, gives rho = 1707 and p = 9e8 Pa at t = 0
+    in the reference's arithmetic too): 200 steps against the chain oracle — integrals within the
+    stated drift, nothing escapes."""
     R = 0.01
     prm = lib_built.default_params(R)
-    fluid = lib_built.scene_block(prm, R, 2.0, R, 0.5)
+    fluid = lib_built.scene_block(prm, 2 * R, 2.0, 2 * R, 0.5)
     boundary = lib_built.scene_boundary(prm)
     sim = lib_built.Simulation(prm)
     sim.upload(fluid, boundary); sim.init_boundary(); sim.compute_accel(*G)
