@@ -77,8 +77,10 @@ typedef struct sphb_stats {
     float min_rho, max_rho;
     unsigned int n_escaped;         /* particles binned by clamping (reference: UB, :111-116) */
     unsigned int max_cell_count;    /* largest cell population at the last build    */
-    unsigned int n_fluid, n_boundary;
+    unsigned int n_fluid, n_boundary; /* on a slab context: particles this rank owns / keeps */
     unsigned long long steps;
+    unsigned int n_lost;            /* slabs: particles that moved > 2 cell columns in one step  */
+    unsigned int n_overflow;        /* slabs: halo message or slot capacity exceeded (fatal)     */
 } sphb_stats;
 
 typedef struct sphb_ctx sphb_ctx;
@@ -168,6 +170,67 @@ void *sphb_stream(sphb_ctx *ctx);
 unsigned long long sphb_launch_count(sphb_ctx *ctx);
 const char *sphb_last_error(void);
 const char *sphb_build_info(void);
+
+/* ---- multi-GPU: x-slabs of whole cell columns (new design, the reference is
+ * single-process) ---------------------------------------------------------------------------
+ *
+ * Rank r of `world` owns the global cell columns [cuts[r], cuts[r+1]) of the reference's grid
+ * (:93-94, cell = 2H) and keeps two ghost columns either side.  Per step each rank sends ONE
+ * message to each neighbour (halo + migrants, 20 B per particle).  Call order per rank:
+ *
+ *   sphb_create -> sphb_mg_configure -> sphb_mg_connect_nccl | sphb_mg_connect_local
+ *   -> sphb_mg_upload (this rank's particles, global ids) -> sphb_init_boundary
+ *   -> sphb_compute_accel / sphb_step / sphb_step_trace        (NCCL transport, one process per GPU)
+ *    | sphb_mg_group_compute_accel / sphb_mg_group_step       (in-process transport, one host thread)
+ *   -> sphb_get_stats (this rank's owned particles) [+ sphb_mg_allreduce_stats | sphb_mg_merge_stats]
+ *   -> sphb_mg_download (owned particles with their global ids)
+ *
+ * In deterministic mode the result is bit-identical to the single-GPU run for any cuts.
+ */
+#define SPHB_NCCL_ID_BYTES 128
+
+typedef struct sphb_mg_info_t {
+    int rank, world;
+    int col_lo, col_hi;             /* owned global columns                         */
+    int window_lo, window_hi;       /* columns held, ghosts included                */
+    int halo_capacity;              /* entries per message                          */
+    int particle_capacity;          /* particle slots on this rank                  */
+    int transport;                  /* 1 NCCL, 2 in-process peer stores             */
+    unsigned long long message_bytes, bytes_sent, exchanges;
+} sphb_mg_info_t;
+
+/* host-side planning (no GPU work): grid shape (:93-94), the global column of x (:112, clamped),
+ * a per-column particle histogram, and cuts at its quantiles (every slab >= min_width columns). */
+int sphb_grid_columns(const sphb_params *prm, int *rows, int *cols);
+int sphb_column_of(const sphb_params *prm, float x);
+int sphb_column_histogram(const sphb_params *prm, const sphb_particle *particles, int n, unsigned long long *hist);
+int sphb_mg_plan_cuts(const unsigned long long *hist, int cols, int world, int min_width, int *cuts /* world+1 */);
+
+int sphb_mg_configure(sphb_ctx *ctx, int rank, int world, int col_lo, int col_hi,
+                      int particle_capacity /* 0: 1.25 n + slack */, int halo_capacity /* 0: 65536 */);
+/* NCCL transport: rank 0 makes an id, the host program broadcasts it (MPI, torch.distributed,
+ * a file...), every rank connects.  libnccl.so.2 is loaded on first use. */
+int sphb_mg_unique_id(char id_out[SPHB_NCCL_ID_BYTES]);
+int sphb_mg_connect_nccl(sphb_ctx *ctx, const char id[SPHB_NCCL_ID_BYTES]);
+/* in-process transport: all ranks' contexts live in this process (same or different GPUs) */
+int sphb_mg_connect_local(sphb_ctx **ctxs, int n);
+
+/* this rank's particles; ids[i] (or id_base + i when ids is NULL) is the particle's global
+ * original index.  The boundary is replicated: pass all of it on every rank. */
+int sphb_mg_upload(sphb_ctx *ctx, const sphb_particle *fluid, const uint32_t *ids, uint32_t id_base, int n_fluid,
+                   const sphb_particle *boundary, int n_boundary);
+/* the particles this rank owns now (any order) with their global ids; *n_out = how many */
+int sphb_mg_download(sphb_ctx *ctx, int cap, sphb_particle *fluid_out, uint32_t *ids_out, float *du_dt,
+                     float *dv_dt, int *n_out);
+
+int sphb_mg_group_compute_accel(sphb_ctx **ctxs, int n, float gravity_x, float gravity_y);
+/* gravity_xy: NULL (constant gravity_x/y) or nsteps (gx, gy) pairs */
+int sphb_mg_group_step(sphb_ctx **ctxs, int n, float gravity_x, float gravity_y, const float *gravity_xy, int nsteps);
+int sphb_mg_group_synchronize(sphb_ctx **ctxs, int n);
+
+int sphb_mg_merge_stats(const sphb_stats *per_rank, int n, sphb_stats *out);
+int sphb_mg_allreduce_stats(sphb_ctx *ctx, sphb_stats *inout);
+int sphb_mg_info(sphb_ctx *ctx, sphb_mg_info_t *out);
 
 /* ---- compat tier: the reference's operator signatures ------------------------------- */
 

@@ -37,6 +37,15 @@ int sphb_scene_fill_boundary(const sphb_params *prm, sphb_particle *boundary_out
 int sphb_gravity_trace_tilt(const sphb_params *prm, float amplitude_deg, int period_steps,
                             int hold_steps, int nsteps, float *gravity_xy_out);
 
+/* slab-wise construction of the block scene (multi-GPU): the particles whose x lies in cell
+ * columns [col_lo, col_hi) — a contiguous index range [*id_base, *id_base + n) of the full scene.
+ * out may be NULL to count only. */
+int sphb_scene_fill_block_slab(const sphb_params *prm, float x0, float x1, float y0, float y1, int col_lo,
+                               int col_hi, sphb_particle *out, unsigned int *id_base);
+/* adds the block scene's per-column particle counts to hist[cols] */
+int sphb_scene_block_column_hist(const sphb_params *prm, float x0, float x1, float y0, float y1,
+                                 unsigned long long *hist);
+
 /* spacing R such that a block of the given area holds about n_target lattice particles */
 float sphb_spacing_for_count(double area, double n_target);
 

@@ -12,6 +12,15 @@ from .api import (  # noqa: F401
     KERNEL_NAMES,
     Params,
     Simulation,
+    Slab,
+    SlabGroup,
+    column_histogram,
+    columns_of,
+    grid_columns,
+    nccl_unique_id,
+    plan_cuts,
+    scene_block_column_hist,
+    scene_block_slab,
     SphbError,
     Stats,
     compat,
@@ -27,7 +36,8 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "PARTICLE", "KERNEL_NAMES", "Params", "Simulation", "SphbError", "Stats", "compat",
+    "PARTICLE", "KERNEL_NAMES", "Params", "Simulation", "Slab", "SlabGroup", "column_histogram", "columns_of",
+    "grid_columns", "nccl_unique_id", "plan_cuts", "scene_block_column_hist", "scene_block_slab", "SphbError", "Stats", "compat",
     "default_params", "gravity_from_raw", "gravity_trace_tilt", "lib", "lib_path",
     "scene_block", "scene_boundary", "scene_drop", "spacing_for_count",
 ]

@@ -45,7 +45,7 @@ class Stats(C.Structure):
         ("max_speed", C.c_float), ("max_rho_err", C.c_float), ("last_rho_err_ref", C.c_float),
         ("min_rho", C.c_float), ("max_rho", C.c_float),
         ("n_escaped", C.c_uint), ("max_cell_count", C.c_uint), ("n_fluid", C.c_uint),
-        ("n_boundary", C.c_uint), ("steps", C.c_ulonglong),
+        ("n_boundary", C.c_uint), ("steps", C.c_ulonglong), ("n_lost", C.c_uint), ("n_overflow", C.c_uint),
     ]
 
     def asdict(self):
@@ -114,6 +114,24 @@ def lib() -> C.CDLL:
         "sphb_scene_fill_boundary": (ci, [vp, vp]),
         "sphb_gravity_trace_tilt": (ci, [vp, cf, ci, ci, ci, vp]),
         "sphb_spacing_for_count": (cf, [C.c_double, C.c_double]),
+        "sphb_scene_fill_block_slab": (ci, [vp, cf, cf, cf, cf, ci, ci, vp, vp]),
+        "sphb_scene_block_column_hist": (ci, [vp, cf, cf, cf, cf, vp]),
+        "sphb_grid_columns": (ci, [vp, vp, vp]),
+        "sphb_column_of": (ci, [vp, cf]),
+        "sphb_column_histogram": (ci, [vp, vp, ci, vp]),
+        "sphb_mg_plan_cuts": (ci, [vp, ci, ci, ci, vp]),
+        "sphb_mg_configure": (ci, [vp, ci, ci, ci, ci, ci, ci]),
+        "sphb_mg_unique_id": (ci, [vp]),
+        "sphb_mg_connect_nccl": (ci, [vp, vp]),
+        "sphb_mg_connect_local": (ci, [vp, ci]),
+        "sphb_mg_upload": (ci, [vp, vp, vp, C.c_uint, ci, vp, ci]),
+        "sphb_mg_download": (ci, [vp, ci, vp, vp, vp, vp, vp]),
+        "sphb_mg_group_compute_accel": (ci, [vp, ci, cf, cf]),
+        "sphb_mg_group_step": (ci, [vp, ci, cf, cf, vp, ci]),
+        "sphb_mg_group_synchronize": (ci, [vp, ci]),
+        "sphb_mg_merge_stats": (ci, [vp, ci, vp]),
+        "sphb_mg_allreduce_stats": (ci, [vp, vp]),
+        "sphb_mg_info": (ci, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -310,6 +328,199 @@ class Simulation:
     @property
     def launch_count(self) -> int:
         return int(lib().sphb_launch_count(self._h))
+
+
+# ------------------------------------------------------------------------------- multi-GPU slabs
+
+class MgInfo(C.Structure):
+    """sphb_mg_info_t (include/sph_b200.h)."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("col_lo", C.c_int), ("col_hi", C.c_int),
+                ("window_lo", C.c_int), ("window_hi", C.c_int), ("halo_capacity", C.c_int),
+                ("particle_capacity", C.c_int), ("transport", C.c_int),
+                ("message_bytes", C.c_ulonglong), ("bytes_sent", C.c_ulonglong), ("exchanges", C.c_ulonglong)]
+
+    def asdict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+NCCL_ID_BYTES = 128
+
+
+def grid_columns(prm: Params):
+    r, c = C.c_int(), C.c_int()
+    _check(lib().sphb_grid_columns(C.byref(prm), C.byref(r), C.byref(c)), "sphb_grid_columns")
+    return r.value, c.value
+
+
+def column_histogram(prm: Params, particles: np.ndarray) -> np.ndarray:
+    _, cols = grid_columns(prm)
+    hist = np.zeros(cols, np.uint64)
+    _check(lib().sphb_column_histogram(C.byref(prm), _p(_particles(particles)), len(particles), _p(hist)),
+           "sphb_column_histogram")
+    return hist
+
+
+def columns_of(prm: Params, x: np.ndarray) -> np.ndarray:
+    """global cell column of each x (pi_sph_fluid.c:112), through the library's own host function"""
+    f = lib().sphb_column_of
+    return np.fromiter((f(C.byref(prm), float(v)) for v in np.asarray(x, np.float32)), np.int32, len(x))
+
+
+def plan_cuts(hist: np.ndarray, world: int, min_width: int = 4) -> np.ndarray:
+    hist = np.ascontiguousarray(hist, np.uint64)
+    cuts = np.zeros(world + 1, np.int32)
+    _check(lib().sphb_mg_plan_cuts(_p(hist), len(hist), world, min_width, _p(cuts)), "sphb_mg_plan_cuts")
+    return cuts
+
+
+def scene_block_column_hist(prm: Params, x0, x1, y0, y1) -> np.ndarray:
+    _, cols = grid_columns(prm)
+    hist = np.zeros(cols, np.uint64)
+    _check(lib().sphb_scene_block_column_hist(C.byref(prm), x0, x1, y0, y1, _p(hist)), "sphb_scene_block_column_hist")
+    return hist
+
+
+def scene_block_slab(prm: Params, x0, x1, y0, y1, col_lo: int, col_hi: int):
+    """-> (particles of the block scene in cell columns [col_lo, col_hi), index of the first one)"""
+    base = C.c_uint()
+    n = _check(lib().sphb_scene_fill_block_slab(C.byref(prm), x0, x1, y0, y1, col_lo, col_hi, None, C.byref(base)),
+               "sphb_scene_fill_block_slab")
+    a = np.zeros(n, PARTICLE)
+    _check(lib().sphb_scene_fill_block_slab(C.byref(prm), x0, x1, y0, y1, col_lo, col_hi, _p(a), C.byref(base)),
+           "sphb_scene_fill_block_slab")
+    return a, int(base.value)
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    _check(lib().sphb_mg_unique_id(buf), "sphb_mg_unique_id")
+    return buf.raw
+
+
+class Slab(Simulation):
+    """One rank of a multi-GPU run: a resident-tier handle restricted to a slab of cell columns."""
+
+    def __init__(self, prm: Params, rank: int, world: int, col_lo: int, col_hi: int,
+                 particle_capacity: int = 0, halo_capacity: int = 0):
+        super().__init__(prm)
+        _check(lib().sphb_mg_configure(self._h, rank, world, col_lo, col_hi, particle_capacity, halo_capacity),
+               "sphb_mg_configure")
+        self.rank, self.world = rank, world
+
+    def connect_nccl(self, unique_id: bytes):
+        _check(lib().sphb_mg_connect_nccl(self._h, C.c_char_p(unique_id)), "sphb_mg_connect_nccl")
+
+    def upload(self, fluid: np.ndarray, boundary: np.ndarray | None = None, ids: np.ndarray | None = None,
+               id_base: int = 0):
+        nb = 0 if boundary is None else len(boundary)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, np.uint32)
+            assert len(ids) == len(fluid)
+        _check(lib().sphb_mg_upload(self._h, _p(_particles(fluid)) if len(fluid) else None, _p(ids), id_base, len(fluid),
+                                    _p(_particles(boundary)) if nb else None, nb), "sphb_mg_upload")
+        self.n_fluid, self.n_boundary = len(fluid), nb
+
+    def download(self, cap: int | None = None, accel: bool = True):
+        """-> (ids, fluid, du, dv) of the particles this rank owns now, sorted by global id"""
+        cap = int(cap if cap is not None else self.info()["particle_capacity"])
+        fluid = np.zeros(cap, PARTICLE)
+        ids = np.zeros(cap, np.uint32)
+        du = np.zeros(cap, np.float32) if accel else None
+        dv = np.zeros(cap, np.float32) if accel else None
+        n = C.c_int()
+        _check(lib().sphb_mg_download(self._h, cap, _p(fluid), _p(ids), _p(du), _p(dv), C.byref(n)), "sphb_mg_download")
+        n = n.value
+        order = np.argsort(ids[:n], kind="stable")
+        return (ids[:n][order], fluid[:n][order], du[:n][order] if accel else None, dv[:n][order] if accel else None)
+
+    def allreduce_stats(self) -> dict:
+        st = Stats()
+        _check(lib().sphb_get_stats(self._h, C.byref(st)), "sphb_get_stats")
+        _check(lib().sphb_mg_allreduce_stats(self._h, C.byref(st)), "sphb_mg_allreduce_stats")
+        return st.asdict()
+
+    def info(self) -> dict:
+        out = MgInfo()
+        _check(lib().sphb_mg_info(self._h, C.byref(out)), "sphb_mg_info")
+        return out.asdict()
+
+
+class SlabGroup:
+    """All slabs of a run inside this process (one host thread drives every GPU): the in-process
+    transport, where the advect+bin kernel stores halo entries straight into the neighbour's
+    receive buffer.  ``devices[r]`` is the CUDA device of slab r (they may coincide)."""
+
+    def __init__(self, prm: Params, cuts, devices=None, particle_capacity: int = 0, halo_capacity: int = 0):
+        world = len(cuts) - 1
+        devices = list(devices) if devices is not None else [prm.device] * world
+        self.cuts = [int(c) for c in cuts]
+        self.slabs = []
+        for r in range(world):
+            p = Params.from_buffer_copy(prm)
+            p.device = devices[r]
+            self.slabs.append(Slab(p, r, world, self.cuts[r], self.cuts[r + 1], particle_capacity, halo_capacity))
+        self._arr = (C.c_void_p * world)(*[s._h for s in self.slabs])
+        _check(lib().sphb_mg_connect_local(self._arr, world), "sphb_mg_connect_local")
+        self.prm = prm
+
+    def close(self):
+        for s in self.slabs:
+            s.close()
+        self.slabs = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def upload(self, fluid: np.ndarray, boundary: np.ndarray | None = None):
+        """Splits the whole scene by owned columns; ids are the indices into `fluid`."""
+        col = columns_of(self.prm, fluid["x"]) if len(fluid) < 200000 else None
+        if col is None:       # vectorised equivalent of sphb_column_of (float32 divide, truncate, clamp)
+            _, cols = grid_columns(self.prm)
+            d = (fluid["x"] - np.float32(self.prm.x_min)) / np.float32(self.prm.cell_length)
+            col = np.clip(d.astype(np.int32), 0, cols - 1)
+        self.n_fluid = len(fluid)
+        for r, s in enumerate(self.slabs):
+            sel = np.nonzero((col >= self.cuts[r]) & (col < self.cuts[r + 1]))[0]
+            s.upload(np.ascontiguousarray(fluid[sel]), boundary, ids=sel.astype(np.uint32))
+
+    def init_boundary(self):
+        for s in self.slabs:
+            s.init_boundary()
+
+    def compute_accel(self, gx: float = 0.0, gy: float = -9.81):
+        _check(lib().sphb_mg_group_compute_accel(self._arr, len(self.slabs), gx, gy), "sphb_mg_group_compute_accel")
+
+    def step(self, nsteps: int = 1, gx: float = 0.0, gy: float = -9.81):
+        _check(lib().sphb_mg_group_step(self._arr, len(self.slabs), gx, gy, None, nsteps), "sphb_mg_group_step")
+
+    def step_trace(self, gravity_xy: np.ndarray):
+        g = np.ascontiguousarray(gravity_xy, np.float32)
+        _check(lib().sphb_mg_group_step(self._arr, len(self.slabs), 0.0, 0.0, _p(g), len(g)), "sphb_mg_group_step")
+
+    def synchronize(self):
+        _check(lib().sphb_mg_group_synchronize(self._arr, len(self.slabs)), "sphb_mg_group_synchronize")
+
+    def download(self):
+        """-> (fluid, du, dv) of the whole scene in original order, plus the owner rank of each particle"""
+        fluid = np.zeros(self.n_fluid, PARTICLE)
+        du = np.zeros(self.n_fluid, np.float32); dv = np.zeros(self.n_fluid, np.float32)
+        owner = np.full(self.n_fluid, -1, np.int32)
+        for r, s in enumerate(self.slabs):
+            ids, f, a, b = s.download()
+            assert (owner[ids] == -1).all(), "a particle is owned by two slabs"
+            fluid[ids] = f; du[ids] = a; dv[ids] = b; owner[ids] = r
+        return fluid, du, dv, owner
+
+    def stats(self) -> dict:
+        per = (Stats * len(self.slabs))()
+        for r, s in enumerate(self.slabs):
+            _check(lib().sphb_get_stats(s._h, C.byref(per[r])), "sphb_get_stats")
+        out = Stats()
+        _check(lib().sphb_mg_merge_stats(per, len(self.slabs), C.byref(out)), "sphb_mg_merge_stats")
+        return out.asdict()
 
 
 # ------------------------------------------------------------------------------- compat tier

@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "libsphb200.so"
 HOST_BIN = PKG / "host" / "sph_b200_main"
 
-SOURCES = ["kernels_build.cu", "kernels_pair.cu", "kernels_aux.cu", "sphb_api.cu", "sphb_compat.cu"]
+SOURCES = ["kernels_build.cu", "kernels_pair.cu", "kernels_aux.cu", "sphb_api.cu", "sphb_compat.cu", "sphb_mg.cu"]
 HEADERS = ["sph_math.cuh", "sph_consts.h", "sphb_internal.cuh"]
 
 NVCC_FLAGS = [
@@ -50,6 +50,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale(LIB, deps):
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES], str(PKG / "host" / "scene.c")]
+    cmd += ["-ldl"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -64,16 +64,30 @@ __device__ __forceinline__ unsigned int float_order_key(float f)
 
 // out_d: [0] sum m, [1] sum m*u, [2] sum m*v, [3] 0.5*sum m*(u^2+v^2)
 // out_u: [0] max speed (float bits, >= 0), [1] key(max rho), [2] key(min rho) (stored inverted),
-//        [3] rho of the particle with the highest original index (what :657-659 reports)
+//        [3] rho of the particle with the highest original index (what :657-659 reports),
+//        [4] particles counted (owned by this rank)
 __global__ void __launch_bounds__(256)
-k_stats(const int n, const float2 *__restrict__ vel, const float2 *__restrict__ rho_prr,
-        const float *__restrict__ mass, const float uniform_mass, const uint32_t *__restrict__ id,
-        double *__restrict__ out_d, unsigned int *__restrict__ out_u)
+k_stats(const Consts k, const Count cnt, const uint32_t last_id, const float2 *__restrict__ vel,
+        const float2 *__restrict__ rho_prr, const float *__restrict__ mass, const float uniform_mass,
+        const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellkey, double *__restrict__ out_d,
+        unsigned int *__restrict__ out_u, const DeviceCounters *__restrict__ ctr,
+        const unsigned int *__restrict__ flags)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // counters of the build / slab kernels: [5] escaped, [6] max cell population, [7] lost, [8] overflow
+        out_u[5] = ctr->n_escaped;
+        out_u[6] = ctr->max_cell_count;
+        out_u[7] = flags ? flags[0] : 0u;
+        out_u[8] = flags ? flags[1] : 0u;
+    }
     double m_sum = 0, mx = 0, my = 0, ke = 0;
     float vmax = 0.0f;
-    unsigned int rmax = 0u, rmin_inv = 0u;
+    unsigned int rmax = 0u, rmin_inv = 0u, owned = 0u;
+    const int n = count_of(cnt);
     for (int s = blockIdx.x * 256 + threadIdx.x; s < n; s += gridDim.x * 256) {
+        // slabs: ghost slots belong to (and are counted by) the neighbouring rank
+        if (cellkey && !owned_col(k, (int)(cellkey[s] & 0xffffu))) continue;
+        ++owned;
         const float2 v = vel[s];
         const float rho = rho_prr[s].x;
         const double m = mass ? (double)mass[s] : (double)uniform_mass;
@@ -86,7 +100,7 @@ k_stats(const int n, const float2 *__restrict__ vel, const float2 *__restrict__ 
         const unsigned int key = float_order_key(rho);
         rmax = key > rmax ? key : rmax;
         rmin_inv = ~key > rmin_inv ? ~key : rmin_inv;
-        if (id[s] == (uint32_t)(n - 1)) out_u[3] = __float_as_uint(rho);
+        if (id[s] == last_id) out_u[3] = __float_as_uint(rho);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -100,6 +114,7 @@ k_stats(const int n, const float2 *__restrict__ vel, const float2 *__restrict__ 
         rmax = o1 > rmax ? o1 : rmax;
         const unsigned int o2 = __shfl_xor_sync(0xffffffffu, rmin_inv, d);
         rmin_inv = o2 > rmin_inv ? o2 : rmin_inv;
+        owned += __shfl_xor_sync(0xffffffffu, owned, d);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&out_d[0], m_sum);
@@ -109,17 +124,20 @@ k_stats(const int n, const float2 *__restrict__ vel, const float2 *__restrict__ 
         atomicMax(&out_u[0], __float_as_uint(vmax));
         atomicMax(&out_u[1], rmax);
         atomicMax(&out_u[2], rmin_inv);
+        if (owned) atomicAdd(&out_u[4], owned);
     }
 }
 
-int launch_stats(cudaStream_t st, const Consts &k, const ParticleSet &f, double *out_d, float *out_u)
+int launch_stats(cudaStream_t st, const Consts &k, const ParticleSet &f, double *out_d, float *out_u,
+                 const DeviceCounters *ctr, const unsigned int *flags)
 {
-    (void)k;
     if (f.n == 0) return 0;
     int grid = (f.n + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
-    k_stats<<<grid, 256, 0, st>>>(f.n, f.vel[f.vc], f.rho_prr, f.uniform_mass ? nullptr : f.mass[f.mc],
-                                  f.uniform_mass_value, f.id[f.ic], out_d, reinterpret_cast<unsigned int *>(out_u));
+    const uint32_t last_id = f.windowed ? 0xffffffffu : (uint32_t)(f.n - 1);
+    k_stats<<<grid, 256, 0, st>>>(k, f.cur(), last_id, f.vel[f.vc], f.rho_prr, f.uniform_mass ? nullptr : f.mass[f.mc],
+                                  f.uniform_mass_value, f.id[f.ic], f.windowed ? f.cellkey : nullptr, out_d,
+                                  reinterpret_cast<unsigned int *>(out_u), ctr, flags);
     return 1;
 }
 

@@ -17,44 +17,146 @@ namespace sphb {
 
 // ------------------------------------------------------------------------ advect + bin
 
-template <bool ADVECT>
-__global__ void __launch_bounds__(kStreamThreads)
-k_advect_bin(const Consts k, const int n, float2 *__restrict__ pos, float2 *__restrict__ vel,
-             const float2 *__restrict__ acc, uint32_t *__restrict__ key, uint32_t *__restrict__ rank,
-             uint32_t *__restrict__ cell_count, DeviceCounters *__restrict__ ctr)
+// Appends (p, v, id) of the lanes with `want` to a halo message: one atomic per warp, the lanes
+// take consecutive entries.  Every lane of the warp must call this.
+__device__ __forceinline__ void slab_append(bool want, uint32_t *cnt, const HaloBuf &b, float2 p, float2 v,
+                                            uint32_t id, unsigned int *overflow)
 {
-    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
-    if (s >= n) return;
-    float2 p = pos[s];
-    if (ADVECT) {
-        float2 v = vel[s];
-        const float2 a = acc[s];
-        v.x = kick(k, v.x, a.x);          // :616
-        v.y = kick(k, v.y, a.y);          // :617
-        p.x = drift(k, p.x, v.x);         // :622
-        p.y = drift(k, p.y, v.y);         // :623
-        vel[s] = v;
-        pos[s] = p;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(cnt, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) {
+        const uint32_t i = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (i < (uint32_t)b.cap) {
+            b.pos()[i] = p;
+            b.vel()[i] = v;
+            b.id()[i] = id;
+        } else {
+            atomicAdd(overflow, 1u);
+        }
     }
-    int row, col;
-    bool clamped;
-    cell_of(k, p.x, p.y, row, col, clamped);          // :111-112
-    if (clamped) atomicAdd(&ctr->n_escaped, 1u);
-    const uint32_t c = (uint32_t)(row * k.cols + col);   // :113
-    key[s] = c;
-    rank[s] = atomicAdd(&cell_count[c], 1u);
 }
 
-int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool advect, DeviceCounters *ctr)
+// SLAB (multi-GPU): slots in ghost columns are dropped (their owner sends them again); owned
+// particles within two columns of a cut — on either side of it, after the drift — are appended to
+// the message for that neighbour: it covers the neighbour's ghost columns and the particles that
+// migrate to it.  Particles whose cell left this rank's window get the trash key.
+template <bool ADVECT, bool SLAB>
+__global__ void __launch_bounds__(kStreamThreads)
+k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *__restrict__ vel,
+             const float2 *__restrict__ acc, const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellkey,
+             uint32_t *__restrict__ key, uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count,
+             DeviceCounters *__restrict__ ctr, const SlabIO io)
+{
+    const int n = count_of(cnt);
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    bool live = s < n;
+    if (SLAB && live && cellkey) live = owned_col(k, (int)(cellkey[s] & 0xffffu));
+    if (SLAB && s < n && !live) key[s] = kTrashKey;
+    float2 p = make_float2(0.0f, 0.0f), v = make_float2(0.0f, 0.0f);
+    int row = 0, col = 0;
+    bool clamped = false, outside = false;
+    if (live) {
+        p = pos[s];
+        if (ADVECT || SLAB) v = vel[s];
+        if (ADVECT) {
+            const float2 a = acc[s];
+            v.x = kick(k, v.x, a.x);          // :616
+            v.y = kick(k, v.y, a.y);          // :617
+            p.x = drift(k, p.x, v.x);         // :622
+            p.y = drift(k, p.y, v.y);         // :623
+            vel[s] = v;
+            pos[s] = p;
+        }
+        cell_of_window(k, p.x, p.y, row, col, clamped, outside);          // :111-112
+        if (clamped) atomicAdd(&ctr->n_escaped, 1u);
+        if (outside) {
+            key[s] = kTrashKey;
+        } else {
+            const uint32_t c = (uint32_t)(row * k.cols + col);   // :113
+            key[s] = c;
+            rank[s] = atomicAdd(&cell_count[c], 1u);
+        }
+    }
+    if (SLAB) {
+        const bool to_left = live && io.has[0] && col < k.own_lo + 2;
+        const bool to_right = live && io.has[1] && col >= k.own_hi - 2;
+        const uint32_t my = (to_left || to_right) ? id[s] : 0u;
+        slab_append(to_left, io.send_cnt[0], io.send[0], p, v, my, io.overflow);
+        slab_append(to_right, io.send_cnt[1], io.send[1], p, v, my, io.overflow);
+        if (live && outside && !to_left && !to_right) atomicAdd(io.lost, 1u);
+    }
+}
+
+int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool advect, DeviceCounters *ctr,
+                      const SlabIO *slab)
 {
     if (ps.n == 0) return 0;
     const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
-    if (advect)
-        k_advect_bin<true><<<grid, kStreamThreads, 0, st>>>(k, ps.n, ps.pos[ps.pc], ps.vel[ps.vc], ps.acc,
-                                                            ps.key, ps.rank, ps.cell_count, ctr);
-    else
-        k_advect_bin<false><<<grid, kStreamThreads, 0, st>>>(k, ps.n, ps.pos[ps.pc], ps.vel[ps.vc], ps.acc,
-                                                             ps.key, ps.rank, ps.cell_count, ctr);
+    const uint32_t *keys = ps.sorted ? ps.cellkey : nullptr;
+#define SPHB_ADV(A, S, IO)                                                                                  \
+    k_advect_bin<A, S><<<grid, kStreamThreads, 0, st>>>(k, ps.cur(), ps.pos[ps.pc], ps.vel[ps.vc], ps.acc,   \
+                                                        ps.id[ps.ic], keys, ps.key, ps.rank, ps.cell_count, ctr, IO)
+    if (slab) { if (advect) SPHB_ADV(true, true, *slab); else SPHB_ADV(false, true, *slab); }
+    else { if (advect) SPHB_ADV(true, false, SlabIO()); else SPHB_ADV(false, false, SlabIO()); }
+#undef SPHB_ADV
+    return 1;
+}
+
+// Received halo / migrant entries become slots n_cur .. n_cur + count_left + count_right - 1 of the
+// build input and are binned like the rest.
+__global__ void __launch_bounds__(kStreamThreads)
+k_bin_recv(const Consts k, const SlabIO io, const int *__restrict__ n_cur, int *__restrict__ n_in,
+           float2 *__restrict__ pos, float2 *__restrict__ vel, uint32_t *__restrict__ id,
+           uint32_t *__restrict__ key, uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count,
+           DeviceCounters *__restrict__ ctr)
+{
+    const uint32_t cap = (uint32_t)io.recv[0].cap;
+    uint32_t cl = io.has[0] ? io.recv[0].hdr()[0] : 0u;
+    uint32_t cr = io.has[1] ? io.recv[1].hdr()[0] : 0u;
+    cl = cl < cap ? cl : cap;
+    cr = cr < cap ? cr : cap;
+    const int n0 = *n_cur;
+    const uint32_t t = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (t == 0) {
+        const long long tot = (long long)n0 + cl + cr;
+        *n_in = tot < io.capacity ? (int)tot : io.capacity;
+        // the messages of this step are out (stream order): restart the send counters
+        if (io.send_cnt[0]) *io.send_cnt[0] = 0u;
+        if (io.send_cnt[1]) *io.send_cnt[1] = 0u;
+    }
+    if (t >= cl + cr) return;
+    const HaloBuf &b = t < cl ? io.recv[0] : io.recv[1];
+    const uint32_t e = t < cl ? t : t - cl;
+    const long long slot = (long long)n0 + t;
+    if (slot >= io.capacity) { atomicAdd(io.overflow, 1u); return; }
+    const float2 p = b.pos()[e];
+    pos[slot] = p;
+    vel[slot] = b.vel()[e];
+    id[slot] = b.id()[e];
+    int row, col;
+    bool clamped, outside;
+    cell_of_window(k, p.x, p.y, row, col, clamped, outside);
+    if (outside) {            // moved more than two columns in one step: nobody keeps it
+        key[slot] = kTrashKey;
+        atomicAdd(io.lost, 1u);
+        return;
+    }
+    const uint32_t c = (uint32_t)(row * k.cols + col);
+    key[slot] = c;
+    rank[slot] = atomicAdd(&cell_count[c], 1u);
+}
+
+int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const SlabIO &slab, DeviceCounters *ctr)
+{
+    const int threads = 2 * slab.recv[0].cap > 0 ? 2 * slab.recv[0].cap : 1;
+    const int grid = (threads + kStreamThreads - 1) / kStreamThreads;
+    k_bin_recv<<<grid, kStreamThreads, 0, st>>>(k, slab, ps.d_n_cur, ps.d_n_in, ps.pos[ps.pc], ps.vel[ps.vc],
+                                                ps.id[ps.ic], ps.key, ps.rank, ps.cell_count, ctr);
     return 1;
 }
 
@@ -83,7 +185,7 @@ __global__ void __launch_bounds__(kScanThreads)
 k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
        unsigned long long *__restrict__ tile_state, unsigned long long *__restrict__ tile_counter,
        const unsigned long long counter_base, const unsigned int epoch, const int n_tiles,
-       DeviceCounters *__restrict__ ctr)
+       DeviceCounters *__restrict__ ctr, int *__restrict__ n_out)
 {
     __shared__ uint32_t s_warp_sum[kScanThreads / 32];
     __shared__ uint32_t s_warp_max[kScanThreads / 32];
@@ -169,7 +271,10 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
 #pragma unroll
             for (int w = 0; w < kScanThreads / 32; w++) m = s_warp_max[w] > m ? s_warp_max[w] : m;
             if (m) atomicMax(&ctr->max_cell_count, m);
-            if ((int)tile == n_tiles - 1) start[n] = excl + aggregate;
+            if ((int)tile == n_tiles - 1) {
+                start[n] = excl + aggregate;
+                if (n_out) *n_out = (int)(excl + aggregate);     // slabs: particles the sort keeps
+            }
         }
     }
     __syncthreads();
@@ -193,7 +298,7 @@ int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc
     if (sc.epoch == 0) sc.epoch = 1;   // 0 is the memset state ("never written")
     const unsigned long long base = sc.launches;   // tiles handed out so far
     k_scan<<<n_tiles, kScanThreads, 0, st>>>(ps.cell_count, ps.cell_start, k.ncells, sc.tile_state,
-                                             sc.tile_counter, base, sc.epoch, n_tiles, ctr);
+                                             sc.tile_counter, base, sc.epoch, n_tiles, ctr, ps.d_n_cur);
     sc.launches += (unsigned long long)n_tiles;
     return 1;
 }
@@ -201,18 +306,20 @@ int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc
 // ------------------------------------------------------------------------ reorder
 
 __global__ void __launch_bounds__(kStreamThreads)
-k_scatter_ids(const int n, const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
+k_scatter_ids(const Count cnt, const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
               const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ start,
               uint32_t *__restrict__ ids_tmp)
 {
     const int s = blockIdx.x * kStreamThreads + threadIdx.x;
-    if (s >= n) return;
-    ids_tmp[start[key[s]] + rank[s]] = id_in[s];
+    if (s >= count_of(cnt)) return;
+    const uint32_t c = key[s];
+    if (c == kTrashKey) return;
+    ids_tmp[start[c] + rank[s]] = id_in[s];
 }
 
 template <bool DET, bool MASS, bool AUX>
 __global__ void __launch_bounds__(kStreamThreads)
-k_reorder(const int n, const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
+k_reorder(const Count cnt, const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
           const uint32_t *__restrict__ start, const uint32_t *__restrict__ ids_tmp,
           const float2 *__restrict__ pos_in, const float2 *__restrict__ vel_in,
           const uint32_t *__restrict__ id_in, const float *__restrict__ mass_in,
@@ -221,8 +328,9 @@ k_reorder(const int n, const uint32_t *__restrict__ key, const uint32_t *__restr
           uint32_t *__restrict__ cellkey_out, const int cols)
 {
     const int s = blockIdx.x * kStreamThreads + threadIdx.x;
-    if (s >= n) return;
+    if (s >= count_of(cnt)) return;
     const uint32_t c = key[s];
+    if (c == kTrashKey) return;      // left this rank's window (slabs) — not carried over
     const uint32_t my = id_in[s];
     const uint32_t b = start[c];
     uint32_t dst;
@@ -248,9 +356,10 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
 {
     if (ps.n == 0) return 0;
     const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
+    const Count in = ps.d_n_in ? ps.in() : ps.cur();
     int launches = 0;
     if (deterministic) {
-        k_scatter_ids<<<grid, kStreamThreads, 0, st>>>(ps.n, ps.key, ps.rank, ps.id[ps.ic], ps.cell_start, ps.ids_tmp);
+        k_scatter_ids<<<grid, kStreamThreads, 0, st>>>(in, ps.key, ps.rank, ps.id[ps.ic], ps.cell_start, ps.ids_tmp);
         launches++;
     }
     const bool has_mass = ps.mass[0] != nullptr;
@@ -260,7 +369,7 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
     const float *aux_in = has_aux ? ps.aux[ps.xc] : nullptr;
     float *aux_out = has_aux ? ps.aux[ps.xc ^ 1] : nullptr;
 #define SPHB_REORDER(D, M, A)                                                                           \
-    k_reorder<D, M, A><<<grid, kStreamThreads, 0, st>>>(ps.n, ps.key, ps.rank, ps.cell_start, ps.ids_tmp, \
+    k_reorder<D, M, A><<<grid, kStreamThreads, 0, st>>>(in, ps.key, ps.rank, ps.cell_start, ps.ids_tmp, \
         ps.pos[ps.pc], ps.vel[ps.vc], ps.id[ps.ic], mass_in, aux_in, ps.pos[ps.pc ^ 1],                  \
         ps.vel[ps.vc ^ 1], ps.id[ps.ic ^ 1], mass_out, aux_out, ps.cellkey, k.cols)
     if (deterministic) {
@@ -287,7 +396,8 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
 
 // AoS `struct particle` (:26-31) -> SoA, identity order
 __global__ void __launch_bounds__(kStreamThreads)
-k_aos_to_soa(const int n, const float *__restrict__ aos, float2 *__restrict__ pos, float2 *__restrict__ vel,
+k_aos_to_soa(const int n, const float *__restrict__ aos, const uint32_t *__restrict__ ids, const uint32_t id_base,
+             float2 *__restrict__ pos, float2 *__restrict__ vel,
              uint32_t *__restrict__ id, float *__restrict__ mass, float *__restrict__ aux,
              float2 *__restrict__ rho_prr, float *__restrict__ p, float2 *__restrict__ acc)
 {
@@ -296,7 +406,7 @@ k_aos_to_soa(const int n, const float *__restrict__ aos, float2 *__restrict__ po
     const float *r = aos + (size_t)i * 7;
     pos[i] = make_float2(r[0], r[1]);
     vel[i] = make_float2(r[2], r[3]);
-    id[i] = (uint32_t)i;
+    id[i] = ids ? ids[i] : id_base + (uint32_t)i;
     if (mass) mass[i] = r[4];
     if (aux) aux[i] = r[5];
     if (rho_prr) rho_prr[i] = make_float2(r[5], 0.0f);
@@ -304,12 +414,15 @@ k_aos_to_soa(const int n, const float *__restrict__ aos, float2 *__restrict__ po
     if (acc) acc[i] = make_float2(0.0f, 0.0f);
 }
 
-int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, bool is_boundary)
+int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, bool is_boundary, int n,
+                      const uint32_t *ids, uint32_t id_base)
 {
-    if (ps.n == 0) return 0;
-    const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
+    if (n < 0) n = ps.n;
     ps.pc = ps.vc = ps.ic = ps.mc = ps.xc = 0;
-    k_aos_to_soa<<<grid, kStreamThreads, 0, st>>>(ps.n, reinterpret_cast<const float *>(aos), ps.pos[0], ps.vel[0],
+    ps.sorted = false;
+    if (n == 0) return 0;
+    const int grid = (n + kStreamThreads - 1) / kStreamThreads;
+    k_aos_to_soa<<<grid, kStreamThreads, 0, st>>>(n, reinterpret_cast<const float *>(aos), ids, id_base, ps.pos[0], ps.vel[0],
                                                   ps.id[0], ps.mass[0], is_boundary ? ps.aux[0] : nullptr,
                                                   is_boundary ? nullptr : ps.rho_prr, is_boundary ? nullptr : ps.p,
                                                   is_boundary ? nullptr : ps.acc);
@@ -348,6 +461,46 @@ int launch_soa_to_aos(cudaStream_t st, const ParticleSet &ps, sphb_particle *aos
         ps.uniform_mass_value, is_boundary ? ps.aux[ps.xc] : nullptr, is_boundary ? nullptr : ps.rho_prr,
         is_boundary ? nullptr : ps.p, ps.acc, reinterpret_cast<float *>(aos), is_boundary ? nullptr : du,
         is_boundary ? nullptr : dv);
+    return 1;
+}
+
+// slabs: the owned particles of this rank, compacted (arrival order), with their global ids
+__global__ void __launch_bounds__(kStreamThreads)
+k_pack_owned(const Consts k, const Count cnt, const float2 *__restrict__ pos, const float2 *__restrict__ vel,
+             const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellkey, const float uniform_mass,
+             const float2 *__restrict__ rho_prr, const float *__restrict__ p, const float2 *__restrict__ acc,
+             const int cap, float *__restrict__ aos, uint32_t *__restrict__ ids_out, float *__restrict__ du,
+             float *__restrict__ dv, unsigned int *__restrict__ n_out)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    const bool mine = s < count_of(cnt) && owned_col(k, (int)(cellkey[s] & 0xffffu));
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(n_out, (unsigned int)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!mine) return;
+    const unsigned int i = base + (unsigned int)__popc(m & ((1u << lane) - 1u));
+    if (i >= (unsigned int)cap) return;
+    float *r = aos + (size_t)i * 7;
+    const float2 x = pos[s], v = vel[s];
+    r[0] = x.x; r[1] = x.y; r[2] = v.x; r[3] = v.y;
+    r[4] = uniform_mass;
+    r[5] = rho_prr[s].x;
+    r[6] = p[s];
+    ids_out[i] = id[s];
+    if (du) { const float2 a = acc[s]; du[i] = a.x; dv[i] = a.y; }
+}
+
+int launch_pack_owned(cudaStream_t st, const Consts &k, const ParticleSet &ps, int cap, sphb_particle *aos,
+                      uint32_t *ids_out, float *du, float *dv, unsigned int *n_out)
+{
+    if (ps.n == 0) return 0;
+    const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
+    k_pack_owned<<<grid, kStreamThreads, 0, st>>>(k, ps.cur(), ps.pos[ps.pc], ps.vel[ps.vc], ps.id[ps.ic], ps.cellkey,
+                                                  ps.uniform_mass_value, ps.rho_prr, ps.p, ps.acc, cap,
+                                                  reinterpret_cast<float *>(aos), ids_out, du, dv, n_out);
     return 1;
 }
 

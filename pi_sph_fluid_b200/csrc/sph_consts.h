@@ -31,6 +31,10 @@ inline Consts make_consts(const sphb_params &p, float uniform_mass)
     k.rows = (int)((p.y_max - p.y_min) / p.cell_length) + 1;     // :93
     k.cols = (int)((p.x_max - p.x_min) / p.cell_length) + 1;     // :94
     k.ncells = k.rows * k.cols;
+    k.gcols = k.cols;
+    k.col_off = 0;
+    k.own_lo = 0;
+    k.own_hi = k.cols;
     k.H = p.H;
     k.inv_H = 1.0f / p.H;
     k.support = 2 * p.H;                                          // :144
@@ -52,6 +56,17 @@ inline Consts make_consts(const sphb_params &p, float uniform_mass)
     k.dt = p.dt;
     k.half_dt = 0.5 * (double)p.dt;                               // :616
     return k;
+}
+
+// Restrict the grid to the window of global columns [win_lo, win_hi) of which [own_lo, own_hi)
+// are owned by this rank (multi-GPU slabs).
+inline void set_window(Consts &k, int win_lo, int win_hi, int own_lo, int own_hi)
+{
+    k.col_off = win_lo;
+    k.cols = win_hi - win_lo;
+    k.ncells = k.rows * k.cols;
+    k.own_lo = own_lo - win_lo;
+    k.own_hi = own_hi - win_lo;
 }
 
 }  // namespace sphb

@@ -14,6 +14,8 @@
 
 namespace sphb {
 
+int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kick2);
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...)
@@ -135,13 +137,45 @@ struct ProfScope {
 // ---- step pieces ----------------------------------------------------------------------
 
 // update_neighbors_context (:104-124) for one set, optionally fused with kick+drift
-int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect)
+int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk)
 {
-    { ProfScope p(c, SPHB_K_ADVECT_BIN); c->launches += launch_advect_bin(c->stream, c->k, ps, advect, c->d_counters); }
-    { ProfScope p(c, SPHB_K_SCAN); c->launches += launch_scan(c->stream, c->k, ps, c->scan, c->d_counters); }
-    { ProfScope p(c, SPHB_K_REORDER); c->launches += launch_reorder(c->stream, c->k, ps, c->prm.deterministic != 0); }
+    const Consts &k = kk ? *kk : c->k;
+    { ProfScope p(c, SPHB_K_ADVECT_BIN); c->launches += launch_advect_bin(c->stream, k, ps, advect, c->d_counters); }
+    { ProfScope p(c, SPHB_K_SCAN); c->launches += launch_scan(c->stream, k, ps, c->scan, c->d_counters); }
+    { ProfScope p(c, SPHB_K_REORDER); c->launches += launch_reorder(c->stream, k, ps, c->prm.deterministic != 0); }
     return SPHB_OK;
 }
+
+// One step in two halves so that a slab exchange fits between them (sphb_mg.cu):
+//   phase A  kick + drift + binning of the resident particles (:615-626); on a slab it also
+//            appends the halo / migration messages for both neighbours
+//   phase B  [slab: bin the received entries] scan, reorder, density+pressure, accelerations, kick
+int step_phase_a(sphb_ctx *c, bool advect)
+{
+    ProfScope p(c, SPHB_K_ADVECT_BIN);
+    if (c->mg.on) {
+        const SlabIO io = mg_slab_io(c);
+        c->launches += launch_advect_bin(c->stream, c->k, c->fluid, advect, c->d_counters, &io);
+    } else {
+        c->launches += launch_advect_bin(c->stream, c->k, c->fluid, advect, c->d_counters);
+    }
+    return SPHB_OK;
+}
+
+int step_phase_b(sphb_ctx *c, float gx, float gy, bool kick2)
+{
+    if (c->mg.on) {
+        ProfScope p(c, SPHB_K_OTHER);
+        const SlabIO io = mg_slab_io(c);
+        c->launches += launch_bin_recv(c->stream, c->k, c->fluid, io, c->d_counters);
+        c->mg.exchanges++;
+    }
+    { ProfScope p(c, SPHB_K_SCAN); c->launches += launch_scan(c->stream, c->k, c->fluid, c->scan, c->d_counters); }
+    { ProfScope p(c, SPHB_K_REORDER); c->launches += launch_reorder(c->stream, c->k, c->fluid, c->prm.deterministic != 0); }
+    return density_force(c, gx, gy, nullptr, kick2);
+}
+
+int free_set_public(ParticleSet &ps) { free_set(ps); return SPHB_OK; }
 
 int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kick2)
 {
@@ -260,6 +294,7 @@ int sphb_destroy(sphb_ctx *c)
     if (!c) return SPHB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    mg_free(c);
     free_set(c->fluid);
     free_set(c->boundary);
     cudaFree(c->d_counters); cudaFree(c->d_gravity); cudaFree(c->d_stage);
@@ -275,6 +310,7 @@ int sphb_destroy(sphb_ctx *c)
 int sphb_upload(sphb_ctx *c, const sphb_particle *fluid, int n_fluid, const sphb_particle *boundary, int n_boundary)
 {
     SPHB_ENTER(c);
+    if (c->mg.on) { set_error("this context is a slab of a multi-GPU run: use sphb_mg_upload"); return SPHB_E_STATE; }
     if (n_fluid < 0 || n_boundary < 0 || (n_fluid > 0 && !fluid) || (n_boundary > 0 && !boundary)) {
         set_error("bad particle arrays"); return SPHB_E_ARG;
     }
@@ -316,6 +352,7 @@ int sphb_upload(sphb_ctx *c, const sphb_particle *fluid, int n_fluid, const sphb
 int sphb_init_boundary(sphb_ctx *c)
 {
     SPHB_ENTER(c);
+    if (c->mg.on) return mg_init_boundary(c);
     if (c->boundary.n > 0) {
         build_grid(c, c->boundary, false);                                        // :600
         ProfScope p(c, SPHB_K_OTHER);
@@ -331,8 +368,16 @@ int sphb_compute_accel(sphb_ctx *c, float gx, float gy)
     SPHB_ENTER(c);
     if (c->fluid.n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
     if (c->boundary.n > 0 && !c->boundary_ready) { set_error("sphb_init_boundary not called"); return SPHB_E_STATE; }
-    build_grid(c, c->fluid, false);                      // :604
-    density_force(c, gx, gy, nullptr, false);            // :605-607
+    if (c->mg.on) {
+        if (c->mg.transport != 1) { set_error("slab not connected over NCCL: use sphb_mg_group_compute_accel"); return SPHB_E_STATE; }
+        step_phase_a(c, false);
+        int rc = mg_exchange_nccl(c);
+        if (rc) return rc;
+        step_phase_b(c, gx, gy, false);
+    } else {
+        build_grid(c, c->fluid, false);                      // :604
+        density_force(c, gx, gy, nullptr, false);            // :605-607
+    }
     c->accel_ready = true;
     SPHB_CUDA(cudaGetLastError());
     return SPHB_OK;
@@ -341,6 +386,7 @@ int sphb_compute_accel(sphb_ctx *c, float gx, float gy)
 int sphb_upload_accel(sphb_ctx *c, const float *du_dt, const float *dv_dt)
 {
     SPHB_ENTER(c);
+    if (c->mg.on) { set_error("not available on a slab context"); return SPHB_E_STATE; }
     const int n = c->fluid.n;
     if (n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
     if (!du_dt || !dv_dt) return SPHB_E_ARG;
@@ -364,10 +410,18 @@ static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int ns
     if (nsteps < 0) return SPHB_E_ARG;
     if (c->fluid.n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
     if (!c->accel_ready) { set_error("sphb_compute_accel must run before sphb_step (:604-607 precede :610)"); return SPHB_E_STATE; }
+    if (c->mg.on && c->mg.transport != 1) { set_error("slab not connected over NCCL: use sphb_mg_group_step"); return SPHB_E_STATE; }
     for (int s = 0; s < nsteps; s++) {
         if (trace) { gx = trace[2 * s]; gy = trace[2 * s + 1]; }    // the value every thread reads at :632
-        build_grid(c, c->fluid, true);                   // :615-626
-        density_force(c, gx, gy, nullptr, true);         // :630-640
+        if (c->mg.on) {
+            step_phase_a(c, true);
+            int rc = mg_exchange_nccl(c);
+            if (rc) return rc;
+            step_phase_b(c, gx, gy, true);
+        } else {
+            build_grid(c, c->fluid, true);                   // :615-626
+            density_force(c, gx, gy, nullptr, true);         // :630-640
+        }
         c->steps++;
     }
     SPHB_CUDA(cudaGetLastError());
@@ -393,6 +447,7 @@ int sphb_synchronize(sphb_ctx *c)
 int sphb_download(sphb_ctx *c, sphb_particle *fluid_out, float *du_dt, float *dv_dt)
 {
     SPHB_ENTER(c);
+    if (c->mg.on) { set_error("this context is a slab of a multi-GPU run: use sphb_mg_download"); return SPHB_E_STATE; }
     const int n = c->fluid.n;
     if (n <= 0) return SPHB_OK;
     if ((du_dt == nullptr) != (dv_dt == nullptr)) { set_error("du_dt and dv_dt go together"); return SPHB_E_ARG; }
@@ -555,31 +610,33 @@ int sphb_get_stats(sphb_ctx *c, sphb_stats *out)
     SPHB_ENTER(c);
     if (!out) return SPHB_E_ARG;
     memset(out, 0, sizeof *out);
-    if (!c->d_stats) SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), 64));
-    struct { double d[4]; unsigned int u[4]; } h;
-    memset(&h, 0, sizeof h);
-    DeviceCounters ctr;
-    memset(&ctr, 0, sizeof ctr);
-    if (c->fluid.n > 0) {
-        SPHB_CUDA(cudaMemsetAsync(c->d_stats, 0, 64, c->stream));
-        c->launches += launch_stats(c->stream, c->k, c->fluid, c->d_stats, reinterpret_cast<float *>(c->d_stats + 4));
-        SPHB_CUDA(cudaMemcpyAsync(&h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-    }
-    SPHB_CUDA(cudaMemcpyAsync(&ctr, c->d_counters, sizeof ctr, cudaMemcpyDeviceToHost, c->stream));
+    // one 128-byte block: 4 doubles | 16 words; read back through pinned memory in one copy
+    struct Block { double d[4]; unsigned int u[16]; };
+    if (!c->d_stats) SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), sizeof(Block)));
+    if (!c->h_pinned) { SPHB_CUDA(cudaMallocHost(&c->h_pinned, 256)); c->pinned_bytes = 256; }
+    Block *h = static_cast<Block *>(c->h_pinned);
+    memset(h, 0, sizeof *h);
+    SPHB_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(Block), c->stream));
+    if (c->fluid.n > 0)
+        c->launches += launch_stats(c->stream, c->k, c->fluid, c->d_stats, reinterpret_cast<float *>(c->d_stats + 4),
+                                    c->d_counters, c->mg.on ? c->mg.d_flags : nullptr);
+    SPHB_CUDA(cudaMemcpyAsync(h, c->d_stats, sizeof(Block), cudaMemcpyDeviceToHost, c->stream));
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
-    out->mass = h.d[0]; out->mom_x = h.d[1]; out->mom_y = h.d[2]; out->kinetic = h.d[3];
-    memcpy(&out->max_speed, &h.u[0], sizeof(float));
-    if (c->fluid.n > 0) {
-        out->max_rho = key_to_float(h.u[1]);
-        out->min_rho = key_to_float(~h.u[2]);
+    out->mass = h->d[0]; out->mom_x = h->d[1]; out->mom_y = h->d[2]; out->kinetic = h->d[3];
+    memcpy(&out->max_speed, &h->u[0], sizeof(float));
+    out->n_fluid = c->mg.on ? h->u[4] : (unsigned int)c->fluid.n;
+    if (out->n_fluid > 0) {
+        out->max_rho = key_to_float(h->u[1]);
+        out->min_rho = key_to_float(~h->u[2]);
         out->max_rho_err = out->max_rho - c->prm.rho0;
         float last;
-        memcpy(&last, &h.u[3], sizeof last);
+        memcpy(&last, &h->u[3], sizeof last);
         out->last_rho_err_ref = last - c->prm.rho0;      // :657-659 as written
     }
-    out->n_escaped = ctr.n_escaped;
-    out->max_cell_count = ctr.max_cell_count;
-    out->n_fluid = (unsigned int)c->fluid.n;
+    out->n_escaped = h->u[5];
+    out->max_cell_count = h->u[6];
+    out->n_lost = h->u[7];
+    out->n_overflow = h->u[8];
     out->n_boundary = (unsigned int)c->boundary.n;
     out->steps = c->steps;
     return SPHB_OK;

@@ -19,6 +19,43 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
+constexpr uint32_t kTrashKey = 0xffffffffu;   // build key of a slot that is dropped by the sort
+
+// Particle count of a launch: `n` sizes the grid (an upper bound when `dev` is set); the kernels
+// use *dev when it is non-null (multi-GPU slabs: counts change on the device every step).
+struct Count {
+    int n;
+    const int *dev;
+};
+__device__ __forceinline__ int count_of(const Count &c)
+{
+    if (!c.dev) return c.n;
+    const int v = *c.dev;
+    return v < c.n ? v : c.n;
+}
+
+// One halo/migration message (sphb_mg.cu): [count, pad x3 | pos[cap] | vel[cap] | id[cap]]
+struct HaloBuf {
+    unsigned char *base = nullptr;
+    int cap = 0;
+    __host__ __device__ uint32_t *hdr() const { return reinterpret_cast<uint32_t *>(base); }
+    __host__ __device__ float2 *pos() const { return reinterpret_cast<float2 *>(base + 16); }
+    __host__ __device__ float2 *vel() const { return pos() + cap; }
+    __host__ __device__ uint32_t *id() const { return reinterpret_cast<uint32_t *>(vel() + cap); }
+    __host__ __device__ size_t bytes() const { return 16 + (size_t)cap * 20; }
+};
+
+// What the slab variant of the build kernels needs (all device pointers; side 0 = left, 1 = right)
+struct SlabIO {
+    uint32_t *send_cnt[2] = {nullptr, nullptr};   // running count of entries appended to send[side]
+    HaloBuf send[2];                              // local send buffer (NCCL) or the peer's recv buffer (direct stores)
+    HaloBuf recv[2];
+    int has[2] = {0, 0};                          // neighbour present on that side
+    unsigned int *lost = nullptr;                 // particles that left the window without a taker
+    unsigned int *overflow = nullptr;             // message or slot capacity exceeded
+    int capacity = 0;                             // allocated particle slots
+};
+
 // A sorted particle set: SoA in HBM, permanently ordered by cell (row-major, the
 // reference's ij_cell = i_cell*m_cells + j_cell, :113).
 struct ParticleSet {
@@ -41,6 +78,12 @@ struct ParticleSet {
     uint32_t *cell_start = nullptr;           // ncells + 1
     bool sorted = false;
     bool uniform_mass = true;
+    // multi-GPU slabs: counts live on the device, `n` is only the launch bound
+    int *d_n_cur = nullptr;                   // valid sorted slots (owned + ghost)
+    int *d_n_in = nullptr;                    // slots feeding the current build (previous + received)
+    bool windowed = false;                    // the grid is a slab window: the sort may drop particles
+    Count cur() const { return Count{n, d_n_cur}; }
+    Count in() const { return Count{n, d_n_in}; }
 };
 
 struct ScanState {
@@ -60,9 +103,31 @@ struct DeviceCounters {        // lives in HBM, read back by sphb_get_stats
     unsigned long long pair_accepted;
 };
 
+// Multi-GPU slab state of one rank (sphb_mg.cu)
+struct MgState {
+    bool on = false;
+    int rank = 0, world = 1;
+    int col_lo = 0, col_hi = 0;          // owned global columns [col_lo, col_hi)
+    int transport = 0;                   // 0: not connected, 1: NCCL (one process per GPU), 2: in-process peers
+    void *nccl_comm = nullptr;           // ncclComm_t
+    int halo_cap = 0;                    // entries per message
+    int capacity = 0;                    // particle slots
+    Consts k_global;                     // the unwindowed grid (boundary pseudo-mass pass)
+    unsigned char *d_send[2] = {nullptr, nullptr};
+    unsigned char *d_recv[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][step parity]
+    uint32_t *d_send_cnt = nullptr;      // 2 words (in-process transport; NCCL counts in the message header)
+    unsigned int *d_flags = nullptr;     // [0] lost, [1] overflow
+    int *d_counts = nullptr;             // [0] n_cur, [1] n_in (fluid), [2] boundary n
+    sphb_ctx *peer[2] = {nullptr, nullptr};
+    cudaEvent_t ev_sent = nullptr;       // phase A of the current step is complete on this rank's stream
+    unsigned long long exchanges = 0;    // step parity for the double-buffered receive side
+    unsigned long long halo_bytes = 0;   // bytes sent so far
+};
+
 }  // namespace sphb
 
 struct sphb_ctx {
+    sphb::MgState mg;
     sphb_params prm;
     sphb::Consts k;
     int device = 0;
@@ -107,10 +172,15 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 // ---- kernel launchers (kernels_build.cu) ---------------------------------------------------
 // All launch on `st`; return the number of kernels launched.
-int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool advect, DeviceCounters *ctr);
+int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool advect, DeviceCounters *ctr,
+                      const SlabIO *slab = nullptr);
+int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const SlabIO &slab, DeviceCounters *ctr);
 int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc, DeviceCounters *ctr);
 int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deterministic);
-int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, bool is_boundary);
+int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, bool is_boundary, int n = -1,
+                      const uint32_t *ids = nullptr, uint32_t id_base = 0);
+int launch_pack_owned(cudaStream_t st, const Consts &k, const ParticleSet &ps, int cap, sphb_particle *aos,
+                      uint32_t *ids_out, float *du, float *dv, unsigned int *n_out);
 int launch_soa_to_aos(cudaStream_t st, const ParticleSet &ps, sphb_particle *aos, float *du, float *dv, bool is_boundary);
 int launch_set_accel(cudaStream_t st, ParticleSet &ps, const float *du, const float *dv);
 int launch_cell_ids(cudaStream_t st, const Consts &k, const ParticleSet &ps, int *cell_out);
@@ -129,13 +199,22 @@ int launch_neighbor_lists(cudaStream_t st, const Consts &k, const ParticleSet &a
 int launch_render(cudaStream_t st, const Consts &k, const ParticleSet &fluid, const float2 *pixels,
                   float W_px, unsigned char *frame);
 int launch_stats(cudaStream_t st, const Consts &k, const ParticleSet &fluid, double *out_d /*4*/,
-                 float *out_u /*4 x 32-bit*/);
+                 float *out_u /*16 x 32-bit*/, const DeviceCounters *ctr, const unsigned int *flags);
 int launch_refresh(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, unsigned int *moved);
 int launch_tait_aos(cudaStream_t st, const Consts &k, int n, sphb_particle *aos);
 
 // ---- host-side helpers (sphb_api.cu) ---------------------------------------------------------
 int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_mass);
 int ensure_stage(sphb_ctx *c, size_t bytes);
-int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect);
+int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk = nullptr);
+int step_phase_a(sphb_ctx *c, bool advect);
+int step_phase_b(sphb_ctx *c, float gx, float gy, bool kick2);
+int free_set_public(ParticleSet &ps);
+
+// sphb_mg.cu
+SlabIO mg_slab_io(const sphb_ctx *c);
+int mg_exchange_nccl(sphb_ctx *c);
+int mg_init_boundary(sphb_ctx *c);
+void mg_free(sphb_ctx *c);
 
 }  // namespace sphb

@@ -115,3 +115,97 @@ float sphb_spacing_for_count(double area, double n_target)
 {
     return (float)sqrt(area / n_target);
 }
+
+/* ---- slab planning (multi-GPU), host side ---------------------------------------------------- */
+
+int sphb_grid_columns(const sphb_params *prm, int *rows, int *cols)
+{
+    if (!prm || !(prm->cell_length > 0)) return SPHB_E_ARG;
+    if (rows) *rows = (int)((prm->y_max - prm->y_min) / prm->cell_length) + 1;     /* :93 */
+    if (cols) *cols = (int)((prm->x_max - prm->x_min) / prm->cell_length) + 1;     /* :94 */
+    return SPHB_OK;
+}
+
+/* :112 — j_cell = (int)((x - x_min)/cell_length), clamped into the grid like the kernels do */
+int sphb_column_of(const sphb_params *prm, float x)
+{
+    int cols = 0;
+    if (sphb_grid_columns(prm, NULL, &cols)) return SPHB_E_ARG;
+    const float d = x - prm->x_min;
+    int c = (int)(d / prm->cell_length);
+    if (c < 0) c = 0;
+    if (c >= cols) c = cols - 1;
+    return c;
+}
+
+int sphb_column_histogram(const sphb_params *prm, const sphb_particle *particles, int n, unsigned long long *hist)
+{
+    int cols = 0;
+    if (!hist || n < 0 || (n > 0 && !particles) || sphb_grid_columns(prm, NULL, &cols)) return SPHB_E_ARG;
+    for (int i = 0; i < n; i++) hist[sphb_column_of(prm, particles[i].x)]++;
+    return SPHB_OK;
+}
+
+/* cuts[r] = first column of rank r: the columns are split at the particle-count quantiles, then
+ * widened so that every slab has at least min_width columns */
+int sphb_mg_plan_cuts(const unsigned long long *hist, int cols, int world, int min_width, int *cuts)
+{
+    if (!hist || !cuts || world < 1 || cols < 1) return SPHB_E_ARG;
+    if (min_width < 1) min_width = 1;
+    if ((long long)world * min_width > cols) return SPHB_E_ARG;
+    unsigned long long total = 0;
+    for (int c = 0; c < cols; c++) total += hist[c];
+    cuts[0] = 0;
+    cuts[world] = cols;
+    unsigned long long acc = 0;
+    int c = 0;
+    for (int r = 1; r < world; r++) {
+        /* smallest cut with at least r/world of the particles to its left */
+        const unsigned long long want = (unsigned long long)(((long double)total * r) / world);
+        while (c < cols && acc < want) acc += hist[c++];
+        cuts[r] = c;
+    }
+    for (int r = 1; r < world; r++)          /* forward: minimum width of slab r-1 */
+        if (cuts[r] < cuts[r - 1] + min_width) cuts[r] = cuts[r - 1] + min_width;
+    for (int r = world - 1; r >= 1; r--)     /* backward: minimum width of slab r */
+        if (cuts[r] > cuts[r + 1] - min_width) cuts[r] = cuts[r + 1] - min_width;
+    return SPHB_OK;
+}
+
+/* block scene restricted to the lattice columns whose x falls into cell columns [col_lo, col_hi):
+ * because the lattice is filled x-outer (like :496-506) that subset is one contiguous range of
+ * the full scene's particle indices; *id_base is its first index. */
+int sphb_scene_fill_block_slab(const sphb_params *prm, float x0, float x1, float y0, float y1, int col_lo,
+                               int col_hi, sphb_particle *out, unsigned int *id_base)
+{
+    if (!prm || !(prm->R > 0)) return SPHB_E_ARG;
+    long long ny = 0;
+    for (float y = 0; y < prm->height; y += prm->R) ny += (y >= y0 && y < y1);
+    long long before = 0, n = 0;
+    for (float x = 0; x < prm->width; x += prm->R) {
+        if (!(x >= x0 && x < x1)) continue;
+        const int col = sphb_column_of(prm, x);
+        if (col < col_lo) { before += ny; continue; }
+        if (col >= col_hi) break;
+        if (out) {
+            for (float y = 0; y < prm->height; y += prm->R)
+                if (y >= y0 && y < y1) out[n++] = fluid_particle(prm, x, y);
+        } else {
+            n += ny;
+        }
+    }
+    if (id_base) *id_base = (unsigned int)before;
+    return n > 2000000000LL ? SPHB_E_ARG : (int)n;
+}
+
+/* per-column particle counts of the block scene without building it */
+int sphb_scene_block_column_hist(const sphb_params *prm, float x0, float x1, float y0, float y1,
+                                 unsigned long long *hist)
+{
+    if (!prm || !hist || !(prm->R > 0)) return SPHB_E_ARG;
+    unsigned long long ny = 0;
+    for (float y = 0; y < prm->height; y += prm->R) ny += (y >= y0 && y < y1);
+    for (float x = 0; x < prm->width; x += prm->R)
+        if (x >= x0 && x < x1) hist[sphb_column_of(prm, x)] += ny;
+    return SPHB_OK;
+}

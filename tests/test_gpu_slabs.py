@@ -1,0 +1,174 @@
+"""Multi-GPU slab path on the GPU box.
+
+The decomposition is exact by construction: in deterministic mode every owned particle sees the
+same neighbours in the same order as in the single-GPU run, so the N-slab result must equal the
+1-GPU result BIT FOR BIT (positions, velocities, rho, p, accelerations), through halo exchange and
+migration.  The in-process transport runs any number of slabs on one device, so these tests need
+one GPU; tests/mg_nccl_check.py covers the NCCL transport on >= 2 GPUs (run under torchrun; the
+pytest wrapper below launches it when two devices are visible).
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import same_bits
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+FIELDS = ("x", "y", "u", "v", "m", "rho", "p")
+
+
+def single_gpu(pkg, prm, fluid, boundary, steps, g):
+    with pkg.Simulation(prm) as sim:
+        sim.upload(fluid, boundary)
+        sim.init_boundary()
+        sim.compute_accel(*g)
+        sim.step(steps, *g)
+        f, du, dv = sim.download()
+        st = sim.stats()
+    return f, du, dv, st
+
+
+def assert_identical(f, du, dv, rf, rdu, rdv):
+    for fld in FIELDS:
+        assert same_bits(f[fld], rf[fld]), fld
+    assert same_bits(du, rdu) and same_bits(dv, rdv)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_slabs_equal_single_gpu_bit_for_bit_drop(lib_built, world):
+    pkg = lib_built
+    prm = pkg.default_params(0.02)
+    fluid, boundary = pkg.scene_drop(prm), pkg.scene_boundary(prm)
+    g = (80.0, -9.81)                    # strong sideways pull: ~1 cell of drift, particles cross the cuts
+    steps = 600
+    rf, rdu, rdv, rst = single_gpu(pkg, prm, fluid, boundary, steps, g)
+
+    cuts = pkg.plan_cuts(pkg.column_histogram(prm, fluid), world)
+    col0 = pkg.columns_of(prm, fluid["x"])
+    with pkg.SlabGroup(prm, cuts, halo_capacity=4096) as grp:
+        grp.upload(fluid, boundary)
+        grp.init_boundary()
+        grp.compute_accel(*g)
+        grp.step(steps, *g)
+        f, du, dv, owner = grp.download()
+        st = grp.stats()
+    assert (owner >= 0).all()
+    assert_identical(f, du, dv, rf, rdu, rdv)
+    # ownership follows the column of the final position, and some particles changed slab
+    col1 = pkg.columns_of(prm, f["x"])
+    assert np.array_equal(owner, np.searchsorted(cuts, col1, side="right") - 1)
+    assert (np.searchsorted(cuts, col0, side="right") != np.searchsorted(cuts, col1, side="right")).sum() > 0
+    assert st["n_lost"] == 0 and st["n_overflow"] == 0 and st["n_fluid"] == len(fluid)
+    assert st["mass"] == pytest.approx(rst["mass"], rel=1e-12)
+    assert st["kinetic"] == pytest.approx(rst["kinetic"], rel=1e-9)
+    assert st["max_speed"] == rst["max_speed"] and st["max_rho"] == rst["max_rho"] and st["min_rho"] == rst["min_rho"]
+
+
+def test_slabs_dam_break_with_empty_slabs_and_trace(lib_built):
+    """Dam-break block in the left half: quantile cuts leave the last slab wide and empty at t=0;
+    gravity comes from a tilt trace (one sample per step)."""
+    pkg = lib_built
+    R = 0.01
+    prm = pkg.default_params(R)
+    fluid = pkg.scene_block(prm, 2 * R, 1.0, 2 * R, 0.6)
+    boundary = pkg.scene_boundary(prm)
+    steps = 300
+    trace = pkg.gravity_trace_tilt(prm, 25.0, 200, 10, steps)
+    with pkg.Simulation(prm) as sim:
+        sim.upload(fluid, boundary); sim.init_boundary(); sim.compute_accel(float(trace[0][0]), float(trace[0][1]))
+        sim.step_trace(trace)
+        rf, rdu, rdv = sim.download()
+    _, cols = pkg.grid_columns(prm)
+    # hand-made cuts: two slabs inside the block, one straddling its face, one empty
+    cuts = np.array([0, 12, 30, 60, cols], np.int32)
+    with pkg.SlabGroup(prm, cuts, halo_capacity=8192) as grp:
+        grp.upload(fluid, boundary)
+        assert grp.slabs[3].n_fluid == 0
+        grp.init_boundary()
+        grp.compute_accel(float(trace[0][0]), float(trace[0][1]))
+        grp.step_trace(trace)
+        f, du, dv, owner = grp.download()
+        st = grp.stats()
+        info = [s.info() for s in grp.slabs]
+    assert_identical(f, du, dv, rf, rdu, rdv)
+    assert st["n_lost"] == 0 and st["n_overflow"] == 0
+    assert info[1]["window_lo"] == 10 and info[1]["window_hi"] == 32 and info[0]["window_lo"] == 0
+    assert all(i["exchanges"] == steps + 1 for i in info)
+
+
+def test_scene_slab_builder_feeds_slabs_directly(lib_built):
+    """Each rank builds only its own part of the block scene (sphb_scene_fill_block_slab): the
+    union is the full scene, ids are the full scene's indices."""
+    pkg = lib_built
+    R = 0.01
+    prm = pkg.default_params(R)
+    box = (2 * R, 2.0, 2 * R, 0.5)
+    full = pkg.scene_block(prm, *box)
+    boundary = pkg.scene_boundary(prm)
+    cuts = pkg.plan_cuts(pkg.scene_block_column_hist(prm, *box), 4)
+    g = (0.0, -9.81)
+    rf, rdu, rdv, _ = single_gpu(pkg, prm, full, boundary, 50, g)
+    with pkg.SlabGroup(prm, cuts, halo_capacity=8192) as grp:
+        n = 0
+        for r, s in enumerate(grp.slabs):
+            part, base = pkg.scene_block_slab(prm, *box, int(cuts[r]), int(cuts[r + 1]))
+            assert np.array_equal(part, full[base:base + len(part)])
+            s.upload(part, boundary, id_base=base)
+            n += len(part)
+        assert n == len(full)
+        grp.n_fluid = n
+        grp.init_boundary()
+        grp.compute_accel(*g)
+        grp.step(50, *g)
+        f, du, dv, _ = grp.download()
+    assert_identical(f, du, dv, rf, rdu, rdv)
+
+
+def test_slab_overflow_is_reported(lib_built):
+    pkg = lib_built
+    prm = pkg.default_params(0.02)
+    fluid, boundary = pkg.scene_drop(prm), pkg.scene_boundary(prm)
+    cuts = pkg.plan_cuts(pkg.column_histogram(prm, fluid), 2)
+    with pkg.SlabGroup(prm, cuts, halo_capacity=16) as grp:      # far too small for a 2-column halo
+        grp.upload(fluid, boundary)
+        grp.init_boundary()
+        grp.compute_accel(0.0, -9.81)
+        st = grp.stats()
+    assert st["n_overflow"] > 0
+
+
+def test_slab_api_misuse(lib_built):
+    pkg = lib_built
+    prm = pkg.default_params(0.02)
+    _, cols = pkg.grid_columns(prm)
+    with pytest.raises(pkg.SphbError):
+        pkg.Slab(prm, 0, 2, 0, 3)                 # narrower than 4 columns
+    with pytest.raises(pkg.SphbError):
+        pkg.Slab(prm, 0, 2, 4, cols)              # rank 0 must start at column 0
+    s = pkg.Slab(prm, 0, 2, 0, 40)
+    with pytest.raises(pkg.SphbError):
+        pkg.Simulation.upload(s, pkg.scene_drop(prm))     # plain upload on a slab context
+    fluid = pkg.scene_drop(prm)
+    s.upload(fluid[:10], pkg.scene_boundary(prm), ids=np.arange(10))
+    s.init_boundary()
+    with pytest.raises(pkg.SphbError):
+        s.compute_accel(0.0, -9.81)               # world 2, not connected
+    s.close()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_nccl_transport_under_torchrun(lib_built, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(ROOT / "tests" / "mg_nccl_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mg_nccl_check ok" in r.stdout
