@@ -57,6 +57,12 @@ def workload_spec(name: str):
         return dict(name="drop_R0.075_269_fluid (BASELINE configs[0])", R=0.075, scene="drop", ref_tag=None)
     if name == "dam4m":
         return dict(name="dam_break_R0.0005_4M (BASELINE configs[2])", R=0.0005, scene="dam", block=(2.0, 0.5), ref_tag=None)
+    if name.startswith("dam") and name.endswith("m"):
+        # dam break, block x in [2R,2) x y in [2R,1): 2 m^2 -> R = sqrt(2 / N).  dam64m = BASELINE configs[3]
+        n = float(name[3:-1]) * 1e6
+        R = float(np.float32(np.sqrt(2.0 / n)))
+        tag = " (BASELINE configs[3])" if name == "dam64m" else ""
+        return dict(name=f"dam_break_2x1m_block_R{R:.4e}_{name[3:-1]}M{tag}", R=R, scene="dam", block=(2.0, 1.0), ref_tag=None)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -127,7 +133,7 @@ def run_reference(spec, steps: int, warmup: int, budget_s: float = 90.0):
     tag = spec["ref_tag"]
     R = spec["R"]
     if spec["scene"] != "drop":
-        return None
+        return run_reference_block(spec, steps, warmup, budget_s)
     kind = "reference"
     try:
         if not pyoracle.reference_available(tag, "fast"):
@@ -157,6 +163,33 @@ def run_reference(spec, steps: int, warmup: int, budget_s: float = 90.0):
     t = run(n_run)
     return {"value": len(fluid) * n_run / t, "unit": UNIT, "cores": int(cores), "kind": kind,
             "sample": f"{n_run} of {steps} steps of the full {len(fluid)}-particle scene, {t:.2f} s",
+            "ms_per_step": 1e3 * t / n_run, "n_fluid": int(len(fluid)), "steps_run": n_run}
+
+
+def run_reference_block(spec, steps: int, warmup: int, budget_s: float, sample_particles: float = 1.0e6):
+    """Dam-break scenes are not in the reference (its main() hard-codes the drop and R is a macro),
+    so the CPU arm for them is the oracle port (same operators, the reference's shipped -Ofast flags,
+    OpenMP on all host cores) on a BOUNDED SAMPLE: the leftmost part of the same block at the same
+    spacing, about `sample_particles` particles."""
+    from oracle import pyoracle
+    R = spec["R"]
+    o = pyoracle.Oracle(R=R, variant="fast")
+    x1, y1 = spec["block"]
+    ny = max(1.0, (y1 - 2 * R) / R)
+    width = min(x1 - 2 * R, max(8 * 2.6 * R, sample_particles / ny * R))
+    fluid = o.scene_block(2 * R, 2 * R + width, 2 * R, y1)
+    boundary = o.scene_boundary()
+    gb = o.init_boundary(boundary); gf = o.grid(len(fluid))
+    du, dv = o.compute_accel(fluid, boundary, gf, gb, *G)
+
+    def run(n):
+        t0 = time.perf_counter(); o.step(fluid, boundary, gf, gb, du, dv, n, *G); return time.perf_counter() - t0
+    nprobe = max(1, min(warmup, 3))
+    per_step = run(nprobe) / nprobe
+    n_run = int(max(1, min(steps, budget_s / max(per_step, 1e-9))))
+    t = run(n_run)
+    return {"value": len(fluid) * n_run / t, "unit": UNIT, "cores": int(o.threads), "kind": "port",
+            "sample": f"{n_run} steps of a {len(fluid)}-particle sub-block (x in [2R, 2R+{width:.4f}) of the same block, same R), {t:.2f} s",
             "ms_per_step": 1e3 * t / n_run, "n_fluid": int(len(fluid)), "steps_run": n_run}
 
 
@@ -308,11 +341,171 @@ def run_gpu(args, spec, rank, world):
     return line
 
 
+def run_gpu_slabs(args, spec, rank, world):
+    """N > 1: the dam-break block cut into x-slabs at the particle-count quantiles, one process per GPU,
+    halo + migration over NCCL (sphb_mg_*).  Weak scaling: the workload has 8M particles per GPU."""
+    import torch
+    import torch.distributed as dist
+    import pi_sph_fluid_b200 as pkg
+
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    R = spec["R"]
+    prm = pkg.default_params(R, deterministic=not args.nondeterministic, device=dev)
+    x1, y1 = spec["block"]
+    box = (2 * R, x1, 2 * R, y1)
+    hist = pkg.scene_block_column_hist(prm, *box)
+    cuts = pkg.plan_cuts(hist, world)
+    n_total = int(hist.sum())
+    part, base = pkg.scene_block_slab(prm, *box, int(cuts[rank]), int(cuts[rank + 1]))
+    boundary = pkg.scene_boundary(prm)
+    n = len(part)
+    halo_est = int(hist[max(int(cuts[rank]) - 2, 0):int(cuts[rank]) + 2].sum() + hist[int(cuts[rank + 1]) - 2:int(cuts[rank + 1]) + 2].sum())
+    halo_cap = max(8192, 2 * max(int(h) for h in [halo_est]))
+    cap_t = torch.tensor([halo_cap], device=f"cuda:{dev}")
+    dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+    halo_cap = int(cap_t.item())
+    K, W = args.steps, max(args.warmup, 3)
+
+    ident = [pkg.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+
+    def make():
+        s_ = pkg.Slab(prm, rank, world, int(cuts[rank]), int(cuts[rank + 1]), halo_capacity=halo_cap)
+        return s_
+    sim = make()
+    sim.connect_nccl(ident[0])
+    stream = torch.cuda.ExternalStream(sim.stream, device=dev)
+    fl_pin = torch.empty(max(n, 1) * 7, dtype=torch.float32).pin_memory()
+    fl_host = fl_pin.numpy().view(pkg.PARTICLE)[:n]
+    fl_host[:] = part
+    sim.upload(fl_host, boundary, id_base=base)
+    sim.init_boundary()
+    sim.compute_accel(*G)
+    clocks = ClockSampler(dev)           # from the warm-up on: the timed region alone may be shorter than a sample
+    clocks.start()
+    sim.step(max(W, 100), *G)
+    sim.synchronize()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=f"cuda:{dev}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: K steps between barriers, CUDA events on the library's stream, max over ranks
+    launches0 = sim.launch_count
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    a.record(stream)
+    sim.step(K, *G)
+    b.record(stream)
+    sim.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    gpu_ms = max_over_ranks(a.elapsed_time(b))
+    launches = sim.launch_count - launches0
+    clk = clocks.stop()
+    value = n_total * K / (gpu_ms * 1e-3)
+
+    # ---- per-kernel CUDA-event times on this rank (separate pass)
+    cand, acc = sim.pair_stats()
+    sim.profile(1); sim.profile_read(reset=True)
+    sim.step(min(K, 20), *G)
+    prof = sim.profile_read(reset=True)
+    sim.profile(0)
+    st = sim.allreduce_stats()
+    info = sim.info()
+    n_local = sim.stats()["n_fluid"]
+    hbm_peak, sm_max_mhz, peak_src = read_peaks()
+    kern = {}
+    for name, d in prof.items():
+        if d["launches"]:
+            ms = d["ms"] / d["launches"]
+            kern[name] = {"ms": round(ms, 5)}
+            if name in ALGO_BYTES:
+                kern[name]["algo_GBps"] = round(ALGO_BYTES[name] * n_local / (ms * 1e-3) / 1e9, 2)
+    force_ms = prof["force"]["ms"] / max(1, prof["force"]["launches"])
+    dens_ms = prof["density"]["ms"] / max(1, prof["density"]["launches"])
+    achieved = ALGO_BYTES["force"] * n_local / (force_ms * 1e-3) / 1e9
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    roofline = {
+        "kernel": "k_force (rank 0)", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
+        "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_particle": ALGO_BYTES["force"],
+        "note": "k_force and k_density are FP32-issue-bound, not HBM-bound (SURVEY.md §8d); see fp32",
+        "fp32": {"force_TFLOPs": round((6 * cand + 44 * acc) * n_local / (force_ms * 1e-3) / 1e12, 3),
+                 "density_TFLOPs": round((6 * cand + 13 * acc) * n_local / (dens_ms * 1e-3) / 1e12, 3),
+                 "peak_TFLOPs": round(fp32_peak, 1),
+                 "force_frac": round((6 * cand + 44 * acc) * n_local / (force_ms * 1e-3) / 1e12 / fp32_peak, 4),
+                 "density_frac": round((6 * cand + 13 * acc) * n_local / (dens_ms * 1e-3) / 1e12 / fp32_peak, 4),
+                 "pairs_per_particle": {"candidates": round(cand, 2), "accepted": round(acc, 2)}},
+        "kernels": kern,
+    }
+
+    # ---- e2e: host buffers -> C ABI -> host buffers on every rank
+    pcap = info["particle_capacity"]
+    out_host = torch.empty(pcap * 7, dtype=torch.float32).pin_memory().numpy().view(pkg.PARTICLE)
+    ids_host = torch.empty(pcap, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    du_host = torch.empty(pcap, dtype=torch.float32).pin_memory().numpy()
+    dv_host = torch.empty(pcap, dtype=torch.float32).pin_memory().numpy()
+    sim2 = make()
+    ident2 = [pkg.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident2, src=0)
+    sim2.connect_nccl(ident2[0])
+    sim2.upload(fl_host, boundary, id_base=base); sim2.init_boundary(); sim2.compute_accel(*G); sim2.step(W, *G); sim2.synchronize()
+    trace = np.tile(np.asarray([G], np.float32), (K, 1))
+    barrier()
+    t0 = time.perf_counter()
+    sim2.upload(fl_host, boundary, id_base=base)
+    sim2.init_boundary()
+    sim2.compute_accel(*G)
+    last = None
+    for s_ in range(K):
+        sim2.step_trace(trace[s_:s_ + 1])
+        last = sim2.stats()
+    n_out = sim2.download_into(out_host, ids_host, du_host, dv_host)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert n_out > 0 or n == 0
+    n_max = int(max_over_ranks(n))
+    e2e = {"value": n_total * K / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": round(28 * (n_max + len(boundary)) / K + 8, 1),
+           "d2h_bytes_per_step": round(40 * n_max / K + 128, 1), "ms_per_step": round(1e3 * e2e_s / K, 5),
+           "path": "per rank: sphb_mg_upload + K x (sphb_step_trace(1) + sphb_get_stats) + sphb_mg_download, pinned host buffers; bytes are the busiest rank's",
+           "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
+    sim2.close()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (dam-break block on the reference's lattice idiom; not a reference scene)",
+        "config": {"workload": spec["name"], "n_fluid": n_total, "n_boundary": int(len(boundary)), "R": R,
+                   "particles_per_gpu": [int(hist[int(cuts[r]):int(cuts[r + 1])].sum()) for r in range(world)],
+                   "parallelism": f"x-slabs of cell columns, cuts at particle-count quantiles {[int(c) for c in cuts]}, "
+                                  "2 ghost columns, one halo+migration message per neighbour per step over NCCL",
+                   "halo_message_bytes": info["message_bytes"], "deterministic_order": not args.nondeterministic,
+                   "l2": "not flushed: per-GPU state (~100 B x 8M particles) is far larger than the 126 MB L2",
+                   "timing": "CUDA events on the library stream around the K steps, barrier + synchronize both sides; max over ranks",
+                   "wall_s_timed_region": round(t_wall, 4),
+                   "merged_stats": {k2: st[k2] for k2 in ("n_fluid", "n_lost", "n_overflow", "n_escaped", "max_speed", "max_rho_err")},
+                   "build": pkg.lib().sphb_build_info().decode()},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    sim.close()
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--nondeterministic", action="store_true")
@@ -321,7 +514,12 @@ def main():
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    spec = workload_spec(args.workload or "drop256k")
+    if args.steps is None:
+        args.steps = 500 if world == 1 else 200
+    if args.warmup is None:
+        args.warmup = 20 if world == 1 else 10
+    # N = 1: BASELINE configs[1].  N > 1: dam break with 8M particles per GPU (N = 8 is configs[3], 64M)
+    spec = workload_spec(args.workload or ("drop256k" if world == 1 else f"dam{8 * world}m"))
 
     if args.impl == "reference":
         if rank != 0:
@@ -333,7 +531,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic (the reference's own lattice drop scene)",
+                "data": ("synthetic (the reference's own lattice drop scene)" if spec["scene"] == "drop" else
+                         "synthetic (dam-break block on the reference's lattice idiom; bounded sub-block sample)"),
                 "config": {"workload": spec["name"], "n_fluid": r["n_fluid"], "R": spec["R"],
                            "threads": r["cores"], "flags": "-Ofast -march=x86-64-v3|v4 -fopenmp (Makefile:2,4; -march pinned for portability)"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -346,8 +545,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     if world > 1:
-        torch.distributed.init_process_group("nccl")
-    line = run_gpu(args, spec, rank, world)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+    line = run_gpu_slabs(args, spec, rank, world) if world > 1 else run_gpu(args, spec, rank, world)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             r = run_reference(spec, 2000, 3, budget_s=15.0)

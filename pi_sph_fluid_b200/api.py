@@ -433,6 +433,13 @@ class Slab(Simulation):
         order = np.argsort(ids[:n], kind="stable")
         return (ids[:n][order], fluid[:n][order], du[:n][order] if accel else None, dv[:n][order] if accel else None)
 
+    def download_into(self, fluid: np.ndarray, ids: np.ndarray, du: np.ndarray | None, dv: np.ndarray | None) -> int:
+        """Owned particles into caller buffers (e.g. pinned), arrival order; returns how many."""
+        n = C.c_int()
+        _check(lib().sphb_mg_download(self._h, len(fluid), _p(_particles(fluid)), _p(ids), _p(du), _p(dv), C.byref(n)),
+               "sphb_mg_download")
+        return n.value
+
     def allreduce_stats(self) -> dict:
         st = Stats()
         _check(lib().sphb_get_stats(self._h, C.byref(st)), "sphb_get_stats")

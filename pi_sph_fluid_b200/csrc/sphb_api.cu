@@ -541,9 +541,12 @@ int sphb_pair_stats(sphb_ctx *c, double *cand, double *acc)
     // a counting density pass writes the same rho/p it would anyway
     c->launches += launch_density(c->stream, c->k, c->fluid, c->boundary, c->d_counters, true);
     SPHB_CUDA(cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    int n = c->fluid.n;
+    if (c->fluid.d_n_cur) SPHB_CUDA(cudaMemcpyAsync(&n, c->fluid.d_n_cur, sizeof n, cudaMemcpyDeviceToHost, c->stream));
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
-    if (cand) *cand = (double)h.pair_candidates / c->fluid.n;
-    if (acc) *acc = (double)h.pair_accepted / c->fluid.n;
+    if (n < 1) n = 1;
+    if (cand) *cand = (double)h.pair_candidates / n;
+    if (acc) *acc = (double)h.pair_accepted / n;
     return SPHB_OK;
 }
 
