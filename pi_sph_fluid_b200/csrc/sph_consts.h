@@ -21,6 +21,28 @@ inline float host_W(float H, float r)
     return nf * powf(a, 4) * b;
 }
 
+// Is  q0 = r*y, q = q0 + fma(-q0, H, r)*y  (y = RN(1/H)) the correctly rounded r/H for every r?
+// The expression is invariant under scaling r by 2, so all 2^23 mantissas of one binade decide it.
+inline bool markstein_div_exact(float H)
+{
+    static float cached_H = 0.0f;
+    static bool cached = false;
+    if (H == cached_H) return cached;
+    const float y = 1.0f / H;
+    bool ok = true;
+    for (unsigned m = 0; m < (1u << 23) && ok; m++) {
+        const unsigned bits = 0x3f800000u | m;
+        float r;
+        memcpy(&r, &bits, sizeof r);
+        const float q0 = r * y;
+        const float q = fmaf(fmaf(-q0, H, r), y, q0);
+        ok = (q == r / H);
+    }
+    cached_H = H;
+    cached = ok;
+    return ok;
+}
+
 inline Consts make_consts(const sphb_params &p, float uniform_mass)
 {
     Consts k;
@@ -47,6 +69,14 @@ inline Consts make_consts(const sphb_params &p, float uniform_mass)
     k.nf = (float)(7 / (4 * M_PI * Hd * Hd));                     // :46
     k.grad_c = (float)(-5.0 * (double)k.nf / (Hd * Hd));
     k.inv_W_ref = 1.0f / host_W(p.H, (float)(0.2 * Hd));          // :325
+    k.div_exact = markstein_div_exact(p.H) ? 1 : 0;
+    {   // corner-cell culling radius: 2H plus 8 ulp of the largest coordinate (covers the rounding
+        // of cell edges and offsets), squared, rounded up
+        const float big = fmaxf(fmaxf(fabsf(p.x_min), fabsf(p.x_max)), fmaxf(fabsf(p.y_min), fabsf(p.y_max)));
+        const float slack = 8.0f * (nextafterf(big, INFINITY) - big);
+        const float rc = k.support + slack;
+        k.cull2 = rc * rc * 1.00001f;
+    }
     k.rho0 = p.rho0;
     k.inv_rho0 = 1.0f / p.rho0;
     k.B = p.c0 * p.c0 * p.rho0 / 7;                               // :297
