@@ -289,6 +289,9 @@ def run_gpu(args, spec, rank, world):
         "kernels": kern,
     }
 
+    if args.no_e2e:
+        sim.close()
+        return {"metric": METRIC, "value": value, "ms_per_step": gpu_ms / K, "roofline": roofline, "tuning_run": True}
     # ---- e2e: host buffers -> C ABI -> host buffers, copies inside the timed region
     fl_pin = torch.empty(n * 7, dtype=torch.float32).pin_memory()
     bd_pin = torch.empty(len(boundary) * 7, dtype=torch.float32).pin_memory()
@@ -510,6 +513,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--nondeterministic", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))

@@ -56,7 +56,9 @@ _LIB = None
 
 
 def lib_path() -> Path:
-    return PKG / "libsphb200.so"
+    import os
+    tag = os.environ.get("SPHB_LIB_VARIANT")        # kernel tuning experiments only (scripts/tune_pair.py)
+    return PKG / (f"libsphb200_{tag}.so" if tag else "libsphb200.so")
 
 
 def lib() -> C.CDLL:

@@ -44,6 +44,18 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
+def build_variant(tag: str, defines: dict) -> Path:
+    """libsphb200_<tag>.so with -DSPHB_* overrides (kernel tuning experiments, scripts/tune_pair.py)."""
+    out = PKG / f"libsphb200_{tag}.so"
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in defines.items()], "-o", str(out),
+           *[str(CSRC / s) for s in SOURCES], str(PKG / "host" / "scene.c"), "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"nvcc failed building variant {tag}")
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     deps = [CSRC / s for s in SOURCES + HEADERS] + [ROOT / "include" / "sph_b200.h", ROOT / "include" / "sph_b200_scene.h",
                                                     PKG / "host" / "scene.c", Path(__file__)]

@@ -168,6 +168,7 @@ k_refresh(const int n, const float *__restrict__ aos, const uint32_t *__restrict
 
 int launch_refresh(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, unsigned int *moved)
 {
+    ps.lists_valid = false;
     if (ps.n == 0) return 0;
     const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
     k_refresh<<<grid, kStreamThreads, 0, st>>>(ps.n, reinterpret_cast<const float *>(aos), ps.id[ps.ic],

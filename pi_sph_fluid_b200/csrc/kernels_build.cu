@@ -389,6 +389,7 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
     if (has_mass) ps.mc ^= 1;
     if (has_aux) ps.xc ^= 1;
     ps.sorted = true;
+    ps.lists_valid = false;          // the handed-over neighbour lists describe the previous order
     return launches;
 }
 
@@ -420,6 +421,7 @@ int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps
     if (n < 0) n = ps.n;
     ps.pc = ps.vc = ps.ic = ps.mc = ps.xc = 0;
     ps.sorted = false;
+    ps.lists_valid = false;
     if (n == 0) return 0;
     const int grid = (n + kStreamThreads - 1) / kStreamThreads;
     k_aos_to_soa<<<grid, kStreamThreads, 0, st>>>(n, reinterpret_cast<const float *>(aos), ids, id_base, ps.pos[0], ps.vel[0],

@@ -39,6 +39,7 @@ static void free_set(ParticleSet &ps)
     }
     cudaFree(ps.acc); cudaFree(ps.rho_prr); cudaFree(ps.p); cudaFree(ps.key); cudaFree(ps.rank);
     cudaFree(ps.ids_tmp); cudaFree(ps.cell_count); cudaFree(ps.cell_start); cudaFree(ps.cellkey);
+    cudaFree(ps.nbr_list); cudaFree(ps.nbr_count); cudaFree(ps.nbr_rows);
     ps = ParticleSet();
 }
 
@@ -73,6 +74,10 @@ int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_ma
         SPHB_CUDA(dmalloc(&ps.rho_prr, m));
         SPHB_CUDA(dmalloc(&ps.p, m));
         SPHB_CUDA(cudaMemset(ps.rho_prr, 0, m * sizeof(float2)));
+        const size_t ctas = ((size_t)n + kPairThreads - 1) / kPairThreads + 1;
+        SPHB_CUDA(dmalloc(&ps.nbr_list, ctas * kListCap * kPairThreads));
+        SPHB_CUDA(dmalloc(&ps.nbr_count, ctas * kPairThreads));
+        SPHB_CUDA(dmalloc(&ps.nbr_rows, ctas));
     }
     SPHB_CUDA(dmalloc(&ps.key, m));
     SPHB_CUDA(dmalloc(&ps.rank, m));
@@ -219,7 +224,11 @@ const char *sphb_last_error(void) { return g_err; }
 
 const char *sphb_build_info(void)
 {
-    return "libsphb200 v1: sm_100a, nvcc " __DATE__ ", pair CTA 128 thr, tile 576, list 48";
+#define SPHB_STR2(x) #x
+#define SPHB_STR(x) SPHB_STR2(x)
+    return "libsphb200 v1: sm_100a, nvcc " __DATE__ ", pair CTA " SPHB_STR(SPHB_PT) " thr, tile " SPHB_STR(SPHB_TILE_CAP)
+           ", lists " SPHB_STR(SPHB_LIST_CAP) "/" SPHB_STR(SPHB_DLIST_CAP) " kind " SPHB_STR(SPHB_DENS_KIND)
+           ", minb " SPHB_STR(SPHB_MINB_D) "/" SPHB_STR(SPHB_MINB_F);
 }
 
 int sphb_default_params(sphb_params *prm, float R, float width, float height)

@@ -11,10 +11,32 @@ namespace sphb {
 
 // ---- tunables ----------------------------------------------------------------------------
 constexpr int kStreamThreads = 256;   // advect/bin, reorder, gather/scatter kernels
-constexpr int kPairThreads = 128;     // density / force CTAs: one thread per particle
-constexpr int kListCap = 48;          // per-thread accepted list entries (u16 tile offsets) before a flush
-constexpr int kDensityListCap = 40;   // same for the density pass's list of f32 squared distances
-constexpr int kTileCap = 576;         // staged neighbourhood entries per CTA (x 8 B must stay < 64 KiB)
+// (the SPHB_* macros exist so that scripts/tune_pair.sh can build variants; defaults are the tuned values)
+#ifndef SPHB_PT
+#define SPHB_PT 128
+#endif
+#ifndef SPHB_LIST_CAP
+#define SPHB_LIST_CAP 48
+#endif
+#ifndef SPHB_DLIST_CAP
+#define SPHB_DLIST_CAP 40
+#endif
+#ifndef SPHB_TILE_CAP
+#define SPHB_TILE_CAP 576
+#endif
+#ifndef SPHB_MINB_D
+#define SPHB_MINB_D 12
+#endif
+#ifndef SPHB_MINB_F
+#define SPHB_MINB_F 8
+#endif
+#ifndef SPHB_DENS_KIND
+#define SPHB_DENS_KIND 0
+#endif
+constexpr int kPairThreads = SPHB_PT;        // density / force CTAs: one thread per particle
+constexpr int kListCap = SPHB_LIST_CAP;      // per-thread accepted list entries (u16 tile offsets) before a flush
+constexpr int kDensityListCap = SPHB_DLIST_CAP;   // same for the density pass's list of f32 squared distances
+constexpr int kTileCap = SPHB_TILE_CAP;      // staged neighbourhood entries per CTA (x 8 B must stay < 64 KiB)
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -78,6 +100,11 @@ struct ParticleSet {
     uint32_t *cell_start = nullptr;           // ncells + 1
     bool sorted = false;
     bool uniform_mass = true;
+    // accepted-neighbour lists handed from the density pass to the force pass of the same step
+    unsigned short *nbr_list = nullptr;       // [CTA][entry < kListCap][thread] tile byte offsets
+    unsigned short *nbr_count = nullptr;      // per sorted slot; 0xffff = search again
+    unsigned int *nbr_rows = nullptr;         // per CTA: rows of its block in use
+    bool lists_valid = false;
     // multi-GPU slabs: counts live on the device, `n` is only the launch bound
     int *d_n_cur = nullptr;                   // valid sorted slots (owned + ghost)
     int *d_n_in = nullptr;                    // slots feeding the current build (previous + received)
