@@ -116,15 +116,28 @@ k_stats(const Consts k, const Count cnt, const uint32_t last_id, const float2 *_
         rmin_inv = o2 > rmin_inv ? o2 : rmin_inv;
         owned += __shfl_xor_sync(0xffffffffu, owned, d);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&out_d[0], m_sum);
-        atomicAdd(&out_d[1], mx);
-        atomicAdd(&out_d[2], my);
-        atomicAdd(&out_d[3], ke);
-        atomicMax(&out_u[0], __float_as_uint(vmax));
-        atomicMax(&out_u[1], rmax);
-        atomicMax(&out_u[2], rmin_inv);
-        if (owned) atomicAdd(&out_u[4], owned);
+    // block level, then ONE set of atomics per CTA: same-address double atomics serialise in L2,
+    // and with one set per warp they — not the reads — set the kernel's duration
+    __shared__ double s_d[8][4];
+    __shared__ unsigned int s_u[8][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        s_d[warp][0] = m_sum; s_d[warp][1] = mx; s_d[warp][2] = my; s_d[warp][3] = ke;
+        s_u[warp][0] = __float_as_uint(vmax); s_u[warp][1] = rmax; s_u[warp][2] = rmin_inv; s_u[warp][3] = owned;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double acc = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) acc += s_d[w][threadIdx.x];
+        atomicAdd(&out_d[threadIdx.x], acc);
+    } else if (threadIdx.x < 8) {
+        const int j = threadIdx.x - 4;
+        unsigned int acc = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) acc = j == 3 ? acc + s_u[w][j] : (s_u[w][j] > acc ? s_u[w][j] : acc);
+        if (j == 3) { if (acc) atomicAdd(&out_u[4], acc); }
+        else atomicMax(&out_u[j], acc);
     }
 }
 
@@ -133,7 +146,7 @@ int launch_stats(cudaStream_t st, const Consts &k, const ParticleSet &f, double 
 {
     if (f.n == 0) return 0;
     int grid = (f.n + 255) / 256;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > 148 * 4) grid = 148 * 4;
     const uint32_t last_id = f.windowed ? 0xffffffffu : (uint32_t)(f.n - 1);
     k_stats<<<grid, 256, 0, st>>>(k, f.cur(), last_id, f.vel[f.vc], f.rho_prr, f.uniform_mass ? nullptr : f.mass[f.mc],
                                   f.uniform_mass_value, f.id[f.ic], f.windowed ? f.cellkey : nullptr, out_d,

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Where does the end-to-end step time go?  (GPU box)"""
+import sys, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+import pi_sph_fluid_b200 as pkg
+R = float(sys.argv[1]) if len(sys.argv) > 1 else 0.002423
+prm = pkg.default_params(R)
+fluid, boundary = pkg.scene_drop(prm), pkg.scene_boundary(prm)
+sim = pkg.Simulation(prm)
+sim.upload(fluid, boundary); sim.init_boundary(); sim.compute_accel(0.0, -9.81); sim.step(50, 0.0, -9.81); sim.synchronize()
+K = 500
+def timeit(name, f):
+    sim.synchronize(); t0 = time.perf_counter()
+    for _ in range(K): f()
+    sim.synchronize(); dt = (time.perf_counter() - t0) / K * 1e6
+    print(f"{name:40s} {dt:8.1f} us/iter")
+g = np.asarray([[0.0, -9.81]], np.float32)
+timeit("step(1) async (queue K)", lambda: sim.step(1, 0.0, -9.81))
+timeit("step(1) + synchronize", lambda: (sim.step(1, 0.0, -9.81), sim.synchronize()))
+timeit("step_trace(1) + synchronize", lambda: (sim.step_trace(g), sim.synchronize()))
+timeit("step(1) + stats", lambda: (sim.step(1, 0.0, -9.81), sim.stats()))
+timeit("stats only", lambda: sim.stats())
+timeit("synchronize only", lambda: sim.synchronize())
+timeit("step(10) + stats", lambda: (sim.step(10, 0.0, -9.81), sim.stats()))
