@@ -219,6 +219,9 @@ int sphb_mg_connect_local(sphb_ctx **ctxs, int n);
  * original index.  The boundary is replicated: pass all of it on every rank. */
 int sphb_mg_upload(sphb_ctx *ctx, const sphb_particle *fluid, const uint32_t *ids, uint32_t id_base, int n_fluid,
                    const sphb_particle *boundary, int n_boundary);
+/* du_dt/dv_dt of the particles just uploaded (same order): a restart / re-cut continues exactly,
+ * without sphb_compute_accel.  Directly after sphb_mg_upload (and sphb_init_boundary in any order). */
+int sphb_mg_upload_accel(sphb_ctx *ctx, const float *du_dt, const float *dv_dt);
 /* the particles this rank owns now (any order) with their global ids; *n_out = how many */
 int sphb_mg_download(sphb_ctx *ctx, int cap, sphb_particle *fluid_out, uint32_t *ids_out, float *du_dt,
                      float *dv_dt, int *n_out);

@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
         "sphb_mg_connect_local": (ci, [vp, ci]),
         "sphb_mg_upload": (ci, [vp, vp, vp, C.c_uint, ci, vp, ci]),
         "sphb_mg_download": (ci, [vp, ci, vp, vp, vp, vp, vp]),
+        "sphb_mg_upload_accel": (ci, [vp, vp, vp]),
         "sphb_mg_group_compute_accel": (ci, [vp, ci, cf, cf]),
         "sphb_mg_group_step": (ci, [vp, ci, cf, cf, vp, ci]),
         "sphb_mg_group_synchronize": (ci, [vp, ci]),
@@ -435,6 +436,11 @@ class Slab(Simulation):
         order = np.argsort(ids[:n], kind="stable")
         return (ids[:n][order], fluid[:n][order], du[:n][order] if accel else None, dv[:n][order] if accel else None)
 
+    def upload_accel(self, du: np.ndarray, dv: np.ndarray):
+        du = np.ascontiguousarray(du, np.float32); dv = np.ascontiguousarray(dv, np.float32)
+        assert len(du) == len(dv) == self.n_fluid
+        _check(lib().sphb_mg_upload_accel(self._h, _p(du), _p(dv)), "sphb_mg_upload_accel")
+
     def download_into(self, fluid: np.ndarray, ids: np.ndarray, du: np.ndarray | None, dv: np.ndarray | None) -> int:
         """Owned particles into caller buffers (e.g. pinned), arrival order; returns how many."""
         n = C.c_int()
@@ -483,17 +489,37 @@ class SlabGroup:
     def __exit__(self, *exc):
         self.close()
 
-    def upload(self, fluid: np.ndarray, boundary: np.ndarray | None = None):
-        """Splits the whole scene by owned columns; ids are the indices into `fluid`."""
+    def upload(self, fluid: np.ndarray, boundary: np.ndarray | None = None, accel=None):
+        """Splits the whole scene by owned columns; ids are the indices into `fluid`.  `accel` =
+        (du, dv) restores the accelerations too (restart / re-cut)."""
         col = columns_of(self.prm, fluid["x"]) if len(fluid) < 200000 else None
         if col is None:       # vectorised equivalent of sphb_column_of (float32 divide, truncate, clamp)
             _, cols = grid_columns(self.prm)
             d = (fluid["x"] - np.float32(self.prm.x_min)) / np.float32(self.prm.cell_length)
             col = np.clip(d.astype(np.int32), 0, cols - 1)
         self.n_fluid = len(fluid)
+        self._boundary = boundary
         for r, s in enumerate(self.slabs):
             sel = np.nonzero((col >= self.cuts[r]) & (col < self.cuts[r + 1]))[0]
             s.upload(np.ascontiguousarray(fluid[sel]), boundary, ids=sel.astype(np.uint32))
+            if accel is not None:
+                s.upload_accel(accel[0][sel], accel[1][sel])
+
+    def rebalance(self, min_width: int = 4):
+        """Re-cut the slabs at the particle-count quantiles of the CURRENT state (the
+        dam break drains the left slabs).  The state, accelerations included, moves to new slab
+        contexts through the host, so the run continues bit-identically.  Returns the new cuts."""
+        fluid, du, dv, _ = self.download()
+        steps = [s.stats()["steps"] for s in self.slabs]
+        cuts = plan_cuts(column_histogram(self.prm, fluid), len(self.slabs), min_width)
+        devices = [s.prm.device for s in self.slabs]
+        info = self.slabs[0].info()
+        boundary = self._boundary
+        self.close()
+        self.__init__(self.prm, cuts, devices, 0, info["halo_capacity"])
+        self.upload(fluid, boundary, accel=(du, dv))
+        self.init_boundary()
+        return self.cuts
 
     def init_boundary(self):
         for s in self.slabs:

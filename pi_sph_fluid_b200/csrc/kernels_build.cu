@@ -513,14 +513,16 @@ k_set_accel(const int n, const uint32_t *__restrict__ id, const float *__restric
 {
     const int s = blockIdx.x * kStreamThreads + threadIdx.x;
     if (s >= n) return;
-    const uint32_t i = id[s];
+    const uint32_t i = id ? id[s] : (uint32_t)s;      // id == nullptr: du/dv are in slot order
     acc[s] = make_float2(du[i], dv[i]);
 }
 
-int launch_set_accel(cudaStream_t st, ParticleSet &ps, const float *du, const float *dv)
+int launch_set_accel(cudaStream_t st, ParticleSet &ps, const float *du, const float *dv, int n_slots)
 {
-    if (ps.n == 0) return 0;
-    k_set_accel<<<(ps.n + kStreamThreads - 1) / kStreamThreads, kStreamThreads, 0, st>>>(ps.n, ps.id[ps.ic], du, dv, ps.acc);
+    const int n = n_slots >= 0 ? n_slots : ps.n;
+    if (n == 0) return 0;
+    k_set_accel<<<(n + kStreamThreads - 1) / kStreamThreads, kStreamThreads, 0, st>>>(n, n_slots >= 0 ? nullptr : ps.id[ps.ic],
+                                                                                      du, dv, ps.acc);
     return 1;
 }
 

@@ -149,6 +149,7 @@ struct MgState {
     cudaEvent_t ev_sent = nullptr;       // phase A of the current step is complete on this rank's stream
     unsigned long long exchanges = 0;    // step parity for the double-buffered receive side
     unsigned long long halo_bytes = 0;   // bytes sent so far
+    int n_uploaded = 0;                  // particles of the last sphb_mg_upload (slot order until the first sort)
 };
 
 }  // namespace sphb
@@ -209,7 +210,7 @@ int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps
 int launch_pack_owned(cudaStream_t st, const Consts &k, const ParticleSet &ps, int cap, sphb_particle *aos,
                       uint32_t *ids_out, float *du, float *dv, unsigned int *n_out);
 int launch_soa_to_aos(cudaStream_t st, const ParticleSet &ps, sphb_particle *aos, float *du, float *dv, bool is_boundary);
-int launch_set_accel(cudaStream_t st, ParticleSet &ps, const float *du, const float *dv);
+int launch_set_accel(cudaStream_t st, ParticleSet &ps, const float *du, const float *dv, int n_slots = -1);
 int launch_cell_ids(cudaStream_t st, const Consts &k, const ParticleSet &ps, int *cell_out);
 
 // ---- kernel launchers (kernels_pair.cu) ----------------------------------------------------

@@ -368,6 +368,34 @@ int sphb_mg_upload(sphb_ctx *c, const sphb_particle *fluid, const uint32_t *ids,
     }
     c->boundary_ready = false;
     c->accel_ready = false;
+    m.n_uploaded = n_fluid;
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+// Restores du_dt/dv_dt (:492-493) of the particles just uploaded, in the same order, so that a
+// run continues exactly where it was (checkpoint restart, re-cut of the slabs): the next kick uses
+// them.  Must follow sphb_mg_upload directly.
+int sphb_mg_upload_accel(sphb_ctx *c, const float *du_dt, const float *dv_dt)
+{
+    SPHB_ENTER(c);
+    MgState &m = c->mg;
+    if (!m.on) { set_error("not a slab context"); return SPHB_E_STATE; }
+    if (c->fluid.sorted) { set_error("sphb_mg_upload_accel must directly follow sphb_mg_upload"); return SPHB_E_STATE; }
+    const int n = m.n_uploaded;
+    if (n > 0 && (!du_dt || !dv_dt)) return SPHB_E_ARG;
+    if (n > 0) {
+        const size_t db = (size_t)n * sizeof(float);
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));
+        int rc = ensure_stage(c, 2 * db + 64);
+        if (rc) return rc;
+        float *d_du = static_cast<float *>(c->d_stage), *d_dv = d_du + n;
+        SPHB_CUDA(cudaMemcpyAsync(d_du, du_dt, db, cudaMemcpyHostToDevice, c->stream));
+        SPHB_CUDA(cudaMemcpyAsync(d_dv, dv_dt, db, cudaMemcpyHostToDevice, c->stream));
+        c->launches += launch_set_accel(c->stream, c->fluid, d_du, d_dv, n);
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    c->accel_ready = true;
     SPHB_CUDA(cudaGetLastError());
     return SPHB_OK;
 }

@@ -129,6 +129,31 @@ def test_scene_slab_builder_feeds_slabs_directly(lib_built):
     assert_identical(f, du, dv, rf, rdu, rdv)
 
 
+def test_rebalance_recuts_at_current_quantiles_and_continues_exactly(lib_built):
+    """The fluid drifts sideways, the initial cuts go stale; re-cutting mid-run (state + du/dv move to
+    new slab contexts) must not change a single bit of the trajectory."""
+    pkg = lib_built
+    prm = pkg.default_params(0.02)
+    fluid, boundary = pkg.scene_drop(prm), pkg.scene_boundary(prm)
+    g = (120.0, -9.81)
+    rf, rdu, rdv, _ = single_gpu(pkg, prm, fluid, boundary, 900, g)
+    _, cols = pkg.grid_columns(prm)
+    cuts0 = np.array([0, 30, 36, cols], np.int32)            # deliberately lopsided
+    with pkg.SlabGroup(prm, cuts0, halo_capacity=4096) as grp:
+        grp.upload(fluid, boundary)
+        grp.init_boundary()
+        grp.compute_accel(*g)
+        grp.step(500, *g)
+        per0 = [s.stats()["n_fluid"] for s in grp.slabs]
+        cuts1 = grp.rebalance()
+        grp.step(400, *g)
+        f, du, dv, owner = grp.download()
+        per2 = [s.stats()["n_fluid"] for s in grp.slabs]
+    assert_identical(f, du, dv, rf, rdu, rdv)
+    assert list(cuts1) != list(cuts0)
+    assert max(per0) - min(per0) > max(per2) - min(per2)        # better balanced after the re-cut
+
+
 def test_slab_overflow_is_reported(lib_built):
     pkg = lib_built
     prm = pkg.default_params(0.02)
