@@ -131,6 +131,12 @@ int sphb_get_stats(sphb_ctx *ctx, sphb_stats *out);
 
 int sphb_synchronize(sphb_ctx *ctx);
 
+/* State file (the reference has none: its arrays live in malloc'd memory until exit): positions,
+ * velocities, du_dt/dv_dt, the boundary and the parameters.  sphb_load_state returns a context
+ * that continues the run bit-identically (device < 0: the device recorded in the file). */
+int sphb_save_state(sphb_ctx *ctx, const char *path);
+int sphb_load_state(const char *path, int device, sphb_ctx **out);
+
 /* :439-440  raw MPU6050 counts -> gravity vector */
 int sphb_gravity_from_raw(const sphb_params *prm, int accel_x_raw, int accel_y_raw,
                           float *gravity_x, float *gravity_y);

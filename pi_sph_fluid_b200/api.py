@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         "sphb_render": (ci, [vp, vp]),
         "sphb_get_stats": (ci, [vp, vp]),
         "sphb_synchronize": (ci, [vp]),
+        "sphb_save_state": (ci, [vp, C.c_char_p]),
+        "sphb_load_state": (ci, [C.c_char_p, ci, C.POINTER(vp)]),
         "sphb_gravity_from_raw": (ci, [vp, ci, ci, vp, vp]),
         "sphb_cell_ids": (ci, [vp, vp]),
         "sphb_grid_shape": (ci, [vp, vp, vp]),
@@ -264,6 +266,19 @@ class Simulation:
 
     def synchronize(self):
         _check(lib().sphb_synchronize(self._h), "sphb_synchronize")
+
+    def save_state(self, path):
+        _check(lib().sphb_save_state(self._h, str(path).encode()), "sphb_save_state")
+
+    @classmethod
+    def load_state(cls, path, device: int = -1) -> "Simulation":
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        _check(lib().sphb_load_state(str(path).encode(), device, C.byref(self._h)), "sphb_load_state")
+        st = Stats()
+        _check(lib().sphb_get_stats(self._h, C.byref(st)), "sphb_get_stats")
+        self.n_fluid, self.n_boundary, self.prm = st.n_fluid, st.n_boundary, None
+        return self
 
     def download(self, accel: bool = True):
         fluid = np.zeros(self.n_fluid, PARTICLE)

@@ -664,6 +664,95 @@ int sphb_flush_l2(sphb_ctx *c)
     return SPHB_OK;
 }
 
+// ---- state files (the reference keeps its state in malloc'd arrays only) -----
+// Layout: 64-byte header | sphb_params | fluid[n] (struct particle) | du_dt[n] | dv_dt[n] | boundary[nb].
+// Everything a run needs to continue bit-identically: positions, velocities and the accelerations the
+// next kick uses (:616); rho/p/psi are recomputed by the first step / sphb_init_boundary.
+struct StateHeader {
+    char magic[8];                  // "SPHB200\0"
+    uint32_t version, params_bytes;
+    uint32_t n_fluid, n_boundary;
+    unsigned long long steps;
+    uint32_t has_accel, reserved[7];
+};
+static_assert(sizeof(StateHeader) == 64, "header layout");
+
+int sphb_save_state(sphb_ctx *c, const char *path)
+{
+    SPHB_ENTER(c);
+    if (!path) return SPHB_E_ARG;
+    if (c->mg.on) { set_error("save each slab through sphb_mg_download"); return SPHB_E_STATE; }
+    const int n = c->fluid.n, nb = c->boundary.n;
+    sphb_particle *f = static_cast<sphb_particle *>(malloc(sizeof(sphb_particle) * (size_t)(n > 0 ? n : 1)));
+    sphb_particle *b = static_cast<sphb_particle *>(malloc(sizeof(sphb_particle) * (size_t)(nb > 0 ? nb : 1)));
+    float *du = static_cast<float *>(malloc(sizeof(float) * (size_t)(n > 0 ? n : 1)));
+    float *dv = static_cast<float *>(malloc(sizeof(float) * (size_t)(n > 0 ? n : 1)));
+    int rc = (f && b && du && dv) ? SPHB_OK : SPHB_E_NOMEM;
+    if (!rc) rc = sphb_download(c, f, du, dv);
+    if (!rc) rc = sphb_download_boundary(c, b);
+    if (!rc) {
+        StateHeader h;
+        memset(&h, 0, sizeof h);
+        memcpy(h.magic, "SPHB200", 8);
+        h.version = 1; h.params_bytes = (uint32_t)sizeof(sphb_params);
+        h.n_fluid = (uint32_t)n; h.n_boundary = (uint32_t)nb; h.steps = c->steps; h.has_accel = c->accel_ready ? 1u : 0u;
+        FILE *fp = fopen(path, "wb");
+        bool ok = fp != nullptr;
+        ok = ok && fwrite(&h, sizeof h, 1, fp) == 1 && fwrite(&c->prm, sizeof c->prm, 1, fp) == 1;
+        ok = ok && (n == 0 || (fwrite(f, sizeof *f, n, fp) == (size_t)n && fwrite(du, 4, n, fp) == (size_t)n && fwrite(dv, 4, n, fp) == (size_t)n));
+        ok = ok && (nb == 0 || fwrite(b, sizeof *b, nb, fp) == (size_t)nb);
+        if (fp) ok = (fclose(fp) == 0) && ok;
+        if (!ok) { set_error("cannot write state file %s", path); rc = SPHB_E_ARG; }
+    }
+    free(f); free(b); free(du); free(dv);
+    return rc;
+}
+
+int sphb_load_state(const char *path, int device, sphb_ctx **out)
+{
+    if (!path || !out) { set_error("null argument"); return SPHB_E_ARG; }
+    *out = nullptr;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) { set_error("cannot open state file %s", path); return SPHB_E_ARG; }
+    StateHeader h;
+    sphb_params prm;
+    sphb_particle *f = nullptr, *b = nullptr;
+    float *du = nullptr, *dv = nullptr;
+    sphb_ctx *c = nullptr;
+    int rc = SPHB_OK;
+    if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "SPHB200", 8) != 0 || h.version != 1 ||
+        h.params_bytes != sizeof(sphb_params) || fread(&prm, sizeof prm, 1, fp) != 1) {
+        set_error("%s is not a version-1 state file", path);
+        rc = SPHB_E_ARG;
+    }
+    if (!rc) {
+        const size_t n = h.n_fluid, nb = h.n_boundary;
+        f = static_cast<sphb_particle *>(malloc(sizeof(sphb_particle) * (n ? n : 1)));
+        b = static_cast<sphb_particle *>(malloc(sizeof(sphb_particle) * (nb ? nb : 1)));
+        du = static_cast<float *>(malloc(4 * (n ? n : 1)));
+        dv = static_cast<float *>(malloc(4 * (n ? n : 1)));
+        if (!f || !b || !du || !dv) rc = SPHB_E_NOMEM;
+        else if ((n && (fread(f, sizeof *f, n, fp) != n || fread(du, 4, n, fp) != n || fread(dv, 4, n, fp) != n)) ||
+                 (nb && fread(b, sizeof *b, nb, fp) != nb)) {
+            set_error("%s is truncated", path);
+            rc = SPHB_E_ARG;
+        }
+    }
+    fclose(fp);
+    if (!rc) {
+        if (device >= 0) prm.device = device;
+        rc = sphb_create(&prm, &c);
+    }
+    if (!rc) rc = sphb_upload(c, f, (int)h.n_fluid, b, (int)h.n_boundary);
+    // psi is recomputed from the wall particles' rho (:242-261), which the file carries unchanged
+    if (!rc) rc = sphb_init_boundary(c);
+    if (!rc && h.has_accel && h.n_fluid) rc = sphb_upload_accel(c, du, dv);
+    if (!rc) { c->steps = h.steps; *out = c; }
+    else if (c) sphb_destroy(c);
+    free(f); free(b); free(du); free(dv);
+    return rc;
+}
+
 void *sphb_stream(sphb_ctx *c) { return c ? (void *)c->stream : nullptr; }
 unsigned long long sphb_launch_count(sphb_ctx *c) { return c ? c->launches : 0ULL; }
 
