@@ -39,7 +39,7 @@ static void free_set(ParticleSet &ps)
     }
     cudaFree(ps.acc); cudaFree(ps.rho_prr); cudaFree(ps.p); cudaFree(ps.key); cudaFree(ps.rank);
     cudaFree(ps.ids_tmp); cudaFree(ps.cell_count); cudaFree(ps.cell_start); cudaFree(ps.cellkey);
-    cudaFree(ps.nbr_list); cudaFree(ps.nbr_count); cudaFree(ps.nbr_rows);
+    cudaFree(ps.nbr_list); cudaFree(ps.nbr_count); cudaFree(ps.nbr_rows); cudaFree(ps.chunk_queue);
     ps = ParticleSet();
 }
 
@@ -78,6 +78,8 @@ int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_ma
         SPHB_CUDA(dmalloc(&ps.nbr_list, ctas * kListCap * kPairThreads));
         SPHB_CUDA(dmalloc(&ps.nbr_count, ctas * kPairThreads));
         SPHB_CUDA(dmalloc(&ps.nbr_rows, ctas));
+        SPHB_CUDA(dmalloc(&ps.chunk_queue, 2));
+        SPHB_CUDA(cudaMemset(ps.chunk_queue, 0, 2 * sizeof(unsigned long long)));
     }
     SPHB_CUDA(dmalloc(&ps.key, m));
     SPHB_CUDA(dmalloc(&ps.rank, m));
@@ -227,7 +229,7 @@ const char *sphb_build_info(void)
 #define SPHB_STR2(x) #x
 #define SPHB_STR(x) SPHB_STR2(x)
     return "libsphb200 v1: sm_100a, nvcc " __DATE__ ", pair CTA " SPHB_STR(SPHB_PT) " thr, tile " SPHB_STR(SPHB_TILE_CAP)
-           ", lists " SPHB_STR(SPHB_LIST_CAP) "/" SPHB_STR(SPHB_DLIST_CAP) " kind " SPHB_STR(SPHB_DENS_KIND)
+           ", list rows " SPHB_STR(SPHB_LIST_CAP) ", window " SPHB_STR(SPHB_WIN_CAP) ", persistent " SPHB_STR(SPHB_PERSISTENT)
            ", minb " SPHB_STR(SPHB_MINB_D) "/" SPHB_STR(SPHB_MINB_F);
 }
 

@@ -18,11 +18,14 @@ constexpr int kStreamThreads = 256;   // advect/bin, reorder, gather/scatter ker
 #ifndef SPHB_LIST_CAP
 #define SPHB_LIST_CAP 48
 #endif
-#ifndef SPHB_DLIST_CAP
-#define SPHB_DLIST_CAP 40
-#endif
 #ifndef SPHB_TILE_CAP
 #define SPHB_TILE_CAP 576
+#endif
+#ifndef SPHB_WIN_CAP
+#define SPHB_WIN_CAP 96
+#endif
+#ifndef SPHB_PERSISTENT
+#define SPHB_PERSISTENT 0
 #endif
 #ifndef SPHB_MINB_D
 #define SPHB_MINB_D 12
@@ -30,13 +33,10 @@ constexpr int kStreamThreads = 256;   // advect/bin, reorder, gather/scatter ker
 #ifndef SPHB_MINB_F
 #define SPHB_MINB_F 8
 #endif
-#ifndef SPHB_DENS_KIND
-#define SPHB_DENS_KIND 0
-#endif
 constexpr int kPairThreads = SPHB_PT;        // density / force CTAs: one thread per particle
 constexpr int kListCap = SPHB_LIST_CAP;      // per-thread accepted list entries (u16 tile offsets) before a flush
-constexpr int kDensityListCap = SPHB_DLIST_CAP;   // same for the density pass's list of f32 squared distances
 constexpr int kTileCap = SPHB_TILE_CAP;      // staged neighbourhood entries per CTA (x 8 B must stay < 64 KiB)
+constexpr int kWinCap = SPHB_WIN_CAP;        // staged cell_start words per neighbour row of a chunk (multiple of 4)
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -105,6 +105,9 @@ struct ParticleSet {
     unsigned short *nbr_count = nullptr;      // per sorted slot; 0xffff = search again
     unsigned int *nbr_rows = nullptr;         // per CTA: rows of its block in use
     bool lists_valid = false;
+    // chunk tickets of the density [0] and force [1] kernels (kernels_pair.cu: ChunkQueue)
+    unsigned long long *chunk_queue = nullptr;
+    unsigned int queue_epoch = 0;
     // multi-GPU slabs: counts live on the device, `n` is only the launch bound
     int *d_n_cur = nullptr;                   // valid sorted slots (owned + ghost)
     int *d_n_in = nullptr;                    // slots feeding the current build (previous + received)
