@@ -86,11 +86,18 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def wait_first(self, timeout: float = 5.0):
+        """nvidia-smi takes a while to start: block until its first sample (or the timeout)."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+        self.rows.clear()                # that sample predates the load
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -210,8 +217,18 @@ def run_gpu(args, spec, rank, world):
     sim.upload(fluid, boundary)
     sim.init_boundary()
     sim.compute_accel(*G)
+    # clocks / throttle reasons are sampled from here to the end of the per-kernel pass: the K timed
+    # steps alone can be shorter than one nvidia-smi sample, so the sampler also sees the warm-up,
+    # which is stretched to at least 0.4 s of the same steps (same kernels, same load)
+    clocks = ClockSampler(dev)
+    clocks.start()
     sim.step(W, *G)
     sim.synchronize()
+    clocks.wait_first()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.4:
+        sim.step(50, *G)
+        sim.synchronize()
     cand, acc = sim.pair_stats()
 
     def barrier():
@@ -220,8 +237,6 @@ def run_gpu(args, spec, rank, world):
         torch.cuda.synchronize()
 
     # ---- value: K steps, per-step events on the library's stream, L2 flushed between steps
-    clocks = ClockSampler(dev)
-    clocks.start()
     launches0 = sim.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
@@ -236,7 +251,6 @@ def run_gpu(args, spec, rank, world):
     t_wall = time.perf_counter() - t_wall0
     gpu_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = sim.launch_count - launches0
-    clk = clocks.stop()
     if world > 1:
         tmax = torch.tensor([gpu_ms], device=f"cuda:{dev}")
         torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
@@ -259,6 +273,7 @@ def run_gpu(args, spec, rank, world):
         sim.step(1, *G)
     prof = sim.profile_read(reset=True)
     sim.profile(0)
+    clk = clocks.stop()
     hbm_peak, sm_max_mhz, peak_src = read_peaks()
     kern = {}
     for name, d in prof.items():
@@ -387,7 +402,10 @@ def run_gpu_slabs(args, spec, rank, world):
     sim.compute_accel(*G)
     clocks = ClockSampler(dev)           # from the warm-up on: the timed region alone may be shorter than a sample
     clocks.start()
-    sim.step(max(W, 100), *G)
+    sim.step(W, *G)
+    sim.synchronize()
+    clocks.wait_first()
+    sim.step(100, *G)
     sim.synchronize()
 
     def barrier():
