@@ -16,10 +16,10 @@ constexpr int kStreamThreads = 256;   // advect/bin, reorder, gather/scatter ker
 #define SPHB_PT 128
 #endif
 #ifndef SPHB_LIST_CAP
-#define SPHB_LIST_CAP 48
+#define SPHB_LIST_CAP 44
 #endif
 #ifndef SPHB_TILE_CAP
-#define SPHB_TILE_CAP 576
+#define SPHB_TILE_CAP 624
 #endif
 #ifndef SPHB_WIN_CAP
 #define SPHB_WIN_CAP 96
