@@ -318,27 +318,34 @@ def run_gpu(args, spec, rank, world):
     trace = np.tile(np.asarray([G], np.float32), (K, 1))
     sim2 = pkg.Simulation(prm)
     sim2.upload(fl_host, bd_host); sim2.init_boundary(); sim2.compute_accel(*G); sim2.step(W, *G); sim2.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    sim2.upload(fl_host, bd_host)                      # H2D: 28 B x (n_fluid + n_boundary)
-    sim2.init_boundary()
-    sim2.compute_accel(*G)
-    last = None
-    for s in range(K):
-        sim2.step_trace(trace[s:s + 1])                # that step's gravity sample (8 B)
-        last = sim2.stats()                            # D2H read-back of the step's statistics (:656-675)
-    sim2.download_into(out_host, du_pin.numpy(), dv_pin.numpy())     # D2H: 36 B x n_fluid
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        tmax = torch.tensor([e2e_s], device=f"cuda:{dev}")
-        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
-        e2e_s = float(tmax.item())
+    # three repetitions of the whole region, the median is reported (host-side jitter of a shared box
+    # shows up here, not in the device-timed value); all three are listed
+    runs, last = [], None
+    for _rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        sim2.upload(fl_host, bd_host)                      # H2D: 28 B x (n_fluid + n_boundary)
+        sim2.init_boundary()
+        sim2.compute_accel(*G)
+        for s in range(K):
+            # that step's gravity sample in (8 B); the step's statistics (:656-675) out: 136 B written by
+            # the force pass into mapped pinned host memory
+            last = sim2.step_stats(trace[s:s + 1])
+        sim2.download_into(out_host, du_pin.numpy(), dv_pin.numpy())     # D2H: 36 B x n_fluid
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            tmax = torch.tensor([e2e_s], device=f"cuda:{dev}")
+            torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+            e2e_s = float(tmax.item())
+        runs.append(e2e_s)
+    e2e_s = sorted(runs)[1]
     h2d = (28 * (n + len(boundary))) / K + 8
-    d2h = (36 * n) / K + 64 + 24
+    d2h = (36 * n) / K + 136
     e2e = {"value": total_particles * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": round(h2d, 1),
            "d2h_bytes_per_step": round(d2h, 1), "ms_per_step": round(1e3 * e2e_s / K, 5),
-           "path": "sphb_upload + K x (sphb_step_trace(1) + sphb_get_stats) + sphb_download, pinned host buffers",
+           "ms_per_step_runs": [round(1e3 * r / K, 5) for r in runs],
+           "path": "sphb_upload + sphb_init_boundary + sphb_compute_accel + K x sphb_step_stats(1 step) + sphb_download, pinned host buffers; median of 3 repetitions",
            "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
     sim2.close()
 
@@ -481,24 +488,26 @@ def run_gpu_slabs(args, spec, rank, world):
     sim2.connect_nccl(ident2[0])
     sim2.upload(fl_host, boundary, id_base=base); sim2.init_boundary(); sim2.compute_accel(*G); sim2.step(W, *G); sim2.synchronize()
     trace = np.tile(np.asarray([G], np.float32), (K, 1))
-    barrier()
-    t0 = time.perf_counter()
-    sim2.upload(fl_host, boundary, id_base=base)
-    sim2.init_boundary()
-    sim2.compute_accel(*G)
-    last = None
-    for s_ in range(K):
-        sim2.step_trace(trace[s_:s_ + 1])
-        last = sim2.stats()
-    n_out = sim2.download_into(out_host, ids_host, du_host, dv_host)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    runs, last, n_out = [], None, 0
+    for _rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        sim2.upload(fl_host, boundary, id_base=base)
+        sim2.init_boundary()
+        sim2.compute_accel(*G)
+        for s_ in range(K):
+            last = sim2.step_stats(trace[s_:s_ + 1])
+        n_out = sim2.download_into(out_host, ids_host, du_host, dv_host)
+        torch.cuda.synchronize()
+        runs.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_s = sorted(runs)[1]
     assert n_out > 0 or n == 0
     n_max = int(max_over_ranks(n))
     e2e = {"value": n_total * K / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": round(28 * (n_max + len(boundary)) / K + 8, 1),
-           "d2h_bytes_per_step": round(40 * n_max / K + 128, 1), "ms_per_step": round(1e3 * e2e_s / K, 5),
-           "path": "per rank: sphb_mg_upload + K x (sphb_step_trace(1) + sphb_get_stats) + sphb_mg_download, pinned host buffers; bytes are the busiest rank's",
+           "d2h_bytes_per_step": round(40 * n_max / K + 136, 1), "ms_per_step": round(1e3 * e2e_s / K, 5),
+           "ms_per_step_runs": [round(1e3 * r / K, 5) for r in runs],
+           "path": "per rank: sphb_mg_upload + sphb_init_boundary + sphb_compute_accel + K x sphb_step_stats(1 step) + sphb_mg_download, pinned host buffers; bytes are the busiest rank's; median of 3 repetitions",
            "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
     sim2.close()
 

@@ -119,6 +119,13 @@ int sphb_step(sphb_ctx *ctx, float gravity_x, float gravity_y, int nsteps);
  * reference's OpenMP threads read from `g` at :632. */
 int sphb_step_trace(sphb_ctx *ctx, const float *gravity_xy, int nsteps);
 
+/* One iteration of the reference's loop body INCLUDING its statistics scans (:612-675), nsteps
+ * times: like sphb_step_trace, and the statistics of the state after the last step are returned in
+ * *out.  They are reduced by the force pass of that step itself and delivered through mapped pinned
+ * host memory, so this call returns when the step is done without any further copy or kernel;
+ * the values are those sphb_get_stats would return.  nsteps >= 1. */
+int sphb_step_stats(sphb_ctx *ctx, const float *gravity_xy, int nsteps, sphb_stats *out);
+
 /* Copies the state back in ORIGINAL particle order.  Any pointer may be NULL. */
 int sphb_download(sphb_ctx *ctx, sphb_particle *fluid_out, float *du_dt, float *dv_dt);
 int sphb_download_boundary(sphb_ctx *ctx, sphb_particle *boundary_out);

@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
         "sphb_download_boundary": (ci, [vp, vp]),
         "sphb_render": (ci, [vp, vp]),
         "sphb_get_stats": (ci, [vp, vp]),
+        "sphb_step_stats": (ci, [vp, vp, ci, vp]),
         "sphb_synchronize": (ci, [vp]),
         "sphb_save_state": (ci, [vp, C.c_char_p]),
         "sphb_load_state": (ci, [C.c_char_p, ci, C.POINTER(vp)]),
@@ -263,6 +264,14 @@ class Simulation:
         g = np.ascontiguousarray(gravity_xy, np.float32)
         assert g.ndim == 2 and g.shape[1] == 2
         _check(lib().sphb_step_trace(self._h, _p(g), len(g)), "sphb_step_trace")
+
+    def step_stats(self, gravity_xy: np.ndarray) -> dict:      # :612-675
+        """len(gravity_xy) steps; returns the statistics of the state after the last one."""
+        g = np.ascontiguousarray(gravity_xy, np.float32)
+        assert g.ndim == 2 and g.shape[1] == 2 and len(g) >= 1
+        st = Stats()
+        _check(lib().sphb_step_stats(self._h, _p(g), len(g), C.byref(st)), "sphb_step_stats")
+        return st.asdict()
 
     def synchronize(self):
         _check(lib().sphb_synchronize(self._h), "sphb_synchronize")

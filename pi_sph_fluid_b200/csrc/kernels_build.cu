@@ -52,6 +52,8 @@ k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *
              uint32_t *__restrict__ key, uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count,
              DeviceCounters *__restrict__ ctr, const SlabIO io)
 {
+    pdl_trigger();
+    pdl_wait();
     const int n = count_of(cnt);
     const int s = blockIdx.x * kStreamThreads + threadIdx.x;
     bool live = s < n;
@@ -99,8 +101,8 @@ int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool ad
     const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
     const uint32_t *keys = ps.sorted ? ps.cellkey : nullptr;
 #define SPHB_ADV(A, S, IO)                                                                                  \
-    k_advect_bin<A, S><<<grid, kStreamThreads, 0, st>>>(k, ps.cur(), ps.pos[ps.pc], ps.vel[ps.vc], ps.acc,   \
-                                                        ps.id[ps.ic], keys, ps.key, ps.rank, ps.cell_count, ctr, IO)
+    launch_pdl(st, grid, kStreamThreads, k_advect_bin<A, S>, k, ps.cur(), ps.pos[ps.pc], ps.vel[ps.vc], ps.acc, \
+               ps.id[ps.ic], keys, ps.key, ps.rank, ps.cell_count, ctr, IO)
     if (slab) { if (advect) SPHB_ADV(true, true, *slab); else SPHB_ADV(false, true, *slab); }
     else { if (advect) SPHB_ADV(true, false, SlabIO()); else SPHB_ADV(false, false, SlabIO()); }
 #undef SPHB_ADV
@@ -115,6 +117,8 @@ k_bin_recv(const Consts k, const SlabIO io, const int *__restrict__ n_cur, int *
            uint32_t *__restrict__ key, uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count,
            DeviceCounters *__restrict__ ctr)
 {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t cap = (uint32_t)io.recv[0].cap;
     uint32_t cl = io.has[0] ? io.recv[0].hdr()[0] : 0u;
     uint32_t cr = io.has[1] ? io.recv[1].hdr()[0] : 0u;
@@ -155,8 +159,8 @@ int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const Sla
 {
     const int threads = 2 * slab.recv[0].cap > 0 ? 2 * slab.recv[0].cap : 1;
     const int grid = (threads + kStreamThreads - 1) / kStreamThreads;
-    k_bin_recv<<<grid, kStreamThreads, 0, st>>>(k, slab, ps.d_n_cur, ps.d_n_in, ps.pos[ps.pc], ps.vel[ps.vc],
-                                                ps.id[ps.ic], ps.key, ps.rank, ps.cell_count, ctr);
+    launch_pdl(st, grid, kStreamThreads, k_bin_recv, k, slab, ps.d_n_cur, ps.d_n_in, ps.pos[ps.pc], ps.vel[ps.vc],
+               ps.id[ps.ic], ps.key, ps.rank, ps.cell_count, ctr);
     return 1;
 }
 
@@ -191,6 +195,8 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
     __shared__ uint32_t s_warp_max[kScanThreads / 32];
     __shared__ uint32_t s_tile, s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    pdl_wait();
     if (tid == 0) s_tile = (uint32_t)(atomicAdd(tile_counter, 1ULL) - counter_base);
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -297,8 +303,8 @@ int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc
     sc.epoch = (sc.epoch + 1) & 0x3fffffffu;
     if (sc.epoch == 0) sc.epoch = 1;   // 0 is the memset state ("never written")
     const unsigned long long base = sc.launches;   // tiles handed out so far
-    k_scan<<<n_tiles, kScanThreads, 0, st>>>(ps.cell_count, ps.cell_start, k.ncells, sc.tile_state,
-                                             sc.tile_counter, base, sc.epoch, n_tiles, ctr, ps.d_n_cur);
+    launch_pdl(st, n_tiles, kScanThreads, k_scan, ps.cell_count, ps.cell_start, k.ncells, sc.tile_state,
+               sc.tile_counter, base, sc.epoch, n_tiles, ctr, ps.d_n_cur);
     sc.launches += (unsigned long long)n_tiles;
     return 1;
 }
@@ -310,6 +316,8 @@ k_scatter_ids(const Count cnt, const uint32_t *__restrict__ key, const uint32_t 
               const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ start,
               uint32_t *__restrict__ ids_tmp)
 {
+    pdl_trigger();
+    pdl_wait();
     const int s = blockIdx.x * kStreamThreads + threadIdx.x;
     if (s >= count_of(cnt)) return;
     const uint32_t c = key[s];
@@ -327,6 +335,8 @@ k_reorder(const Count cnt, const uint32_t *__restrict__ key, const uint32_t *__r
           uint32_t *__restrict__ id_out, float *__restrict__ mass_out, float *__restrict__ aux_out,
           uint32_t *__restrict__ cellkey_out, const int cols)
 {
+    pdl_trigger();
+    pdl_wait();
     const int s = blockIdx.x * kStreamThreads + threadIdx.x;
     if (s >= count_of(cnt)) return;
     const uint32_t c = key[s];
@@ -359,7 +369,7 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
     const Count in = ps.d_n_in ? ps.in() : ps.cur();
     int launches = 0;
     if (deterministic) {
-        k_scatter_ids<<<grid, kStreamThreads, 0, st>>>(in, ps.key, ps.rank, ps.id[ps.ic], ps.cell_start, ps.ids_tmp);
+        launch_pdl(st, grid, kStreamThreads, k_scatter_ids, in, ps.key, ps.rank, ps.id[ps.ic], ps.cell_start, ps.ids_tmp);
         launches++;
     }
     const bool has_mass = ps.mass[0] != nullptr;
@@ -369,7 +379,7 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
     const float *aux_in = has_aux ? ps.aux[ps.xc] : nullptr;
     float *aux_out = has_aux ? ps.aux[ps.xc ^ 1] : nullptr;
 #define SPHB_REORDER(D, M, A)                                                                           \
-    k_reorder<D, M, A><<<grid, kStreamThreads, 0, st>>>(in, ps.key, ps.rank, ps.cell_start, ps.ids_tmp, \
+    launch_pdl(st, grid, kStreamThreads, k_reorder<D, M, A>, in, ps.key, ps.rank, ps.cell_start, ps.ids_tmp, \
         ps.pos[ps.pc], ps.vel[ps.vc], ps.id[ps.ic], mass_in, aux_in, ps.pos[ps.pc ^ 1],                  \
         ps.vel[ps.vc ^ 1], ps.id[ps.ic ^ 1], mass_out, aux_out, ps.cellkey, k.cols)
     if (deterministic) {

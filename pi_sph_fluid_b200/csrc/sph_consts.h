@@ -69,6 +69,9 @@ inline Consts make_consts(const sphb_params &p, float uniform_mass)
     k.nf = (float)(7 / (4 * M_PI * Hd * Hd));                     // :46
     k.grad_c = (float)(-5.0 * (double)k.nf / (Hd * Hd));
     k.inv_W_ref = 1.0f / host_W(p.H, (float)(0.2 * Hd));          // :325
+    k.a_c = (float)(-0.5 / Hd);
+    k.b_c = (float)(2.0 / Hd);
+    k.art_c = (float)(pow(0.1, 0.25) * (double)k.nf * (double)k.inv_W_ref);
     k.div_exact = markstein_div_exact(p.H) ? 1 : 0;
     {   // corner-cell culling radius: 2H plus 8 ulp of the largest coordinate (covers the rounding
         // of cell edges and offsets), squared, rounded up
@@ -82,6 +85,7 @@ inline Consts make_consts(const sphb_params &p, float uniform_mass)
     k.B = p.c0 * p.c0 * p.rho0 / 7;                               // :297
     k.eps_h2 = (float)(0.01 * Hd * Hd);                           // :332
     k.visc_cH = (float)(-0.01 * (double)p.c0 * Hd);               // :332, :334
+    k.visc2_cH = (float)(-0.02 * (double)p.c0 * Hd);
     k.mass = uniform_mass;
     k.dt = p.dt;
     k.half_dt = 0.5 * (double)p.dt;                               // :616

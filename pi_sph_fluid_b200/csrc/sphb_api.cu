@@ -14,7 +14,7 @@
 
 namespace sphb {
 
-int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kick2);
+int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kick2, const StepStats *ss = nullptr);
 
 static thread_local char g_err[512] = "";
 
@@ -108,6 +108,12 @@ int ensure_stage(sphb_ctx *c, size_t bytes)
     return SPHB_OK;
 }
 
+bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = getenv("SPHB_NO_PDL"); return !(e && *e && *e != '0'); }();
+    return on;
+}
+
 // ---- profiling ------------------------------------------------------------------------
 
 static int prof_drain(sphb_ctx *c)
@@ -169,7 +175,7 @@ int step_phase_a(sphb_ctx *c, bool advect)
     return SPHB_OK;
 }
 
-int step_phase_b(sphb_ctx *c, float gx, float gy, bool kick2)
+int step_phase_b(sphb_ctx *c, float gx, float gy, bool kick2, const StepStats *ss)
 {
     if (c->mg.on) {
         ProfScope p(c, SPHB_K_OTHER);
@@ -179,15 +185,22 @@ int step_phase_b(sphb_ctx *c, float gx, float gy, bool kick2)
     }
     { ProfScope p(c, SPHB_K_SCAN); c->launches += launch_scan(c->stream, c->k, c->fluid, c->scan, c->d_counters); }
     { ProfScope p(c, SPHB_K_REORDER); c->launches += launch_reorder(c->stream, c->k, c->fluid, c->prm.deterministic != 0); }
-    return density_force(c, gx, gy, nullptr, kick2);
+    return density_force(c, gx, gy, nullptr, kick2, ss);
 }
 
 int free_set_public(ParticleSet &ps) { free_set(ps); return SPHB_OK; }
 
-int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kick2)
+int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kick2, const StepStats *ss_in)
 {
-    { ProfScope p(c, SPHB_K_DENSITY); c->launches += launch_density(c->stream, c->k, c->fluid, c->boundary, c->d_counters, false); }
-    { ProfScope p(c, SPHB_K_FORCE); c->launches += launch_force(c->stream, c->k, c->fluid, c->boundary, gx, gy, g_dev, kick2, c->d_counters); }
+    StepStats ss_here;
+    const StepStats *ss = nullptr;
+    if (ss_in) {
+        ss_here = *ss_in;
+        ss_here.id = c->fluid.id[c->fluid.ic];      // the sorted order this step's reorder produced
+        ss = &ss_here;
+    }
+    { ProfScope p(c, SPHB_K_DENSITY); c->launches += launch_density(c->stream, c->k, c->fluid, c->boundary, c->d_counters, false, true, ss ? ss->block : nullptr); }
+    { ProfScope p(c, SPHB_K_FORCE); c->launches += launch_force(c->stream, c->k, c->fluid, c->boundary, gx, gy, g_dev, kick2, c->d_counters, true, ss); }
     return SPHB_OK;
 }
 
@@ -294,6 +307,12 @@ int sphb_create(const sphb_params *prm, sphb_ctx **out)
     SPHB_CUDA(cudaMemset(c->scan.tile_state, 0, sizeof(unsigned long long) * (c->scan.n_tiles + 1)));
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->scan.tile_counter), sizeof(unsigned long long)));
     SPHB_CUDA(cudaMemset(c->scan.tile_counter, 0, sizeof(unsigned long long)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), 128));
+    SPHB_CUDA(cudaMemset(c->d_stats, 0, 128));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats_done), sizeof(unsigned int)));
+    SPHB_CUDA(cudaMemset(c->d_stats_done, 0, sizeof(unsigned int)));
+    SPHB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c->h_stats), 256, cudaHostAllocMapped));
+    memset(c->h_stats, 0, 256);
     for (int i = 0; i < 128; i++) SPHB_CUDA(cudaEventCreate(&c->ev[i]));
     SPHB_CUDA(cudaDeviceSynchronize());      // memsets above vs. the non-blocking stream
     *out = c;
@@ -310,8 +329,9 @@ int sphb_destroy(sphb_ctx *c)
     free_set(c->boundary);
     cudaFree(c->d_counters); cudaFree(c->d_gravity); cudaFree(c->d_stage);
     cudaFree(c->d_pixels); cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_l2_scratch);
-    cudaFree(c->scan.tile_state); cudaFree(c->scan.tile_counter);
+    cudaFree(c->scan.tile_state); cudaFree(c->scan.tile_counter); cudaFree(c->d_stats_done);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
     for (int i = 0; i < 128; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -415,27 +435,66 @@ int sphb_upload_accel(sphb_ctx *c, const float *du_dt, const float *dv_dt)
     return SPHB_OK;
 }
 
-static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int nsteps)
+struct StatsBlock { double d[4]; unsigned int u[16]; };     // the 128-byte block k_stats / k_force<STATS> fill
+static void decode_stats(const sphb_ctx *c, const StatsBlock *h, sphb_stats *out);
+
+// stats_out != NULL: the force pass of the LAST step also reduces the step statistics and its last CTA
+// stores them into mapped host memory; the host waits for the sequence word there (no copy, no
+// stream synchronisation).
+static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int nsteps, sphb_stats *stats_out = nullptr)
 {
     SPHB_ENTER(c);
     if (nsteps < 0) return SPHB_E_ARG;
     if (c->fluid.n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
     if (!c->accel_ready) { set_error("sphb_compute_accel must run before sphb_step (:604-607 precede :610)"); return SPHB_E_STATE; }
     if (c->mg.on && c->mg.transport != 1) { set_error("slab not connected over NCCL: use sphb_mg_group_step"); return SPHB_E_STATE; }
+    StepStats ss;
+    if (stats_out && nsteps > 0) {
+        ss.block = reinterpret_cast<unsigned long long *>(c->d_stats);
+        ss.ctr = c->d_counters;
+        ss.flags = c->mg.on ? c->mg.d_flags : nullptr;
+        ss.last_id = c->fluid.windowed ? 0xffffffffu : (uint32_t)(c->fluid.n - 1);
+        ss.done = c->d_stats_done;
+        ss.host = c->h_stats;
+        ss.seq = ++c->stats_seq;
+    }
     for (int s = 0; s < nsteps; s++) {
         if (trace) { gx = trace[2 * s]; gy = trace[2 * s + 1]; }    // the value every thread reads at :632
+        const bool with_stats = stats_out && s == nsteps - 1;
         if (c->mg.on) {
             step_phase_a(c, true);
             int rc = mg_exchange_nccl(c);
             if (rc) return rc;
-            step_phase_b(c, gx, gy, true);
+            step_phase_b(c, gx, gy, true, with_stats ? &ss : nullptr);
         } else {
             build_grid(c, c->fluid, true);                   // :615-626
-            density_force(c, gx, gy, nullptr, true);         // :630-640
+            density_force(c, gx, gy, nullptr, true, with_stats ? &ss : nullptr);         // :630-640
         }
         c->steps++;
     }
     SPHB_CUDA(cudaGetLastError());
+    if (stats_out && nsteps > 0) {
+        volatile unsigned long long *seq = c->h_stats + 16;
+        unsigned long long spins = 0;
+        while (*seq != ss.seq) {
+            if ((++spins & 0x3ffULL) == 0) {
+                const cudaError_t q = cudaStreamQuery(c->stream);
+                if (q == cudaSuccess) {
+                    if (*seq == ss.seq) break;
+                    set_error("step statistics were not delivered");
+                    return SPHB_E_STATE;
+                }
+                if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery", __FILE__, __LINE__);
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        StatsBlock h;
+        memcpy(&h, c->h_stats, sizeof h);
+        decode_stats(c, &h, stats_out);
+    }
     return SPHB_OK;
 }
 
@@ -445,6 +504,12 @@ int sphb_step_trace(sphb_ctx *c, const float *gravity_xy, int nsteps)
 {
     if (!gravity_xy && nsteps > 0) return SPHB_E_ARG;
     return step_impl(c, 0.0f, 0.0f, gravity_xy, nsteps);
+}
+
+int sphb_step_stats(sphb_ctx *c, const float *gravity_xy, int nsteps, sphb_stats *out)
+{
+    if (!out || nsteps < 1 || !gravity_xy) { set_error("sphb_step_stats: needs nsteps >= 1, a gravity sample per step and an output"); return SPHB_E_ARG; }
+    return step_impl(c, 0.0f, 0.0f, gravity_xy, nsteps, out);
 }
 
 int sphb_synchronize(sphb_ctx *c)
@@ -619,23 +684,9 @@ static float key_to_float(unsigned int key)
     return f;
 }
 
-int sphb_get_stats(sphb_ctx *c, sphb_stats *out)
+static void decode_stats(const sphb_ctx *c, const StatsBlock *h, sphb_stats *out)
 {
-    SPHB_ENTER(c);
-    if (!out) return SPHB_E_ARG;
     memset(out, 0, sizeof *out);
-    // one 128-byte block: 4 doubles | 16 words; read back through pinned memory in one copy
-    struct Block { double d[4]; unsigned int u[16]; };
-    if (!c->d_stats) SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), sizeof(Block)));
-    if (!c->h_pinned) { SPHB_CUDA(cudaMallocHost(&c->h_pinned, 256)); c->pinned_bytes = 256; }
-    Block *h = static_cast<Block *>(c->h_pinned);
-    memset(h, 0, sizeof *h);
-    SPHB_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(Block), c->stream));
-    if (c->fluid.n > 0)
-        c->launches += launch_stats(c->stream, c->k, c->fluid, c->d_stats, reinterpret_cast<float *>(c->d_stats + 4),
-                                    c->d_counters, c->mg.on ? c->mg.d_flags : nullptr);
-    SPHB_CUDA(cudaMemcpyAsync(h, c->d_stats, sizeof(Block), cudaMemcpyDeviceToHost, c->stream));
-    SPHB_CUDA(cudaStreamSynchronize(c->stream));
     out->mass = h->d[0]; out->mom_x = h->d[1]; out->mom_y = h->d[2]; out->kinetic = h->d[3];
     memcpy(&out->max_speed, &h->u[0], sizeof(float));
     out->n_fluid = c->mg.on ? h->u[4] : (unsigned int)c->fluid.n;
@@ -653,6 +704,24 @@ int sphb_get_stats(sphb_ctx *c, sphb_stats *out)
     out->n_overflow = h->u[8];
     out->n_boundary = (unsigned int)c->boundary.n;
     out->steps = c->steps;
+}
+
+int sphb_get_stats(sphb_ctx *c, sphb_stats *out)
+{
+    SPHB_ENTER(c);
+    if (!out) return SPHB_E_ARG;
+    memset(out, 0, sizeof *out);
+    // one 128-byte block: 4 doubles | 16 words; read back through pinned memory in one copy
+    if (!c->h_pinned) { SPHB_CUDA(cudaMallocHost(&c->h_pinned, 256)); c->pinned_bytes = 256; }
+    StatsBlock *h = static_cast<StatsBlock *>(c->h_pinned);
+    memset(h, 0, sizeof *h);
+    SPHB_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsBlock), c->stream));
+    if (c->fluid.n > 0)
+        c->launches += launch_stats(c->stream, c->k, c->fluid, c->d_stats, reinterpret_cast<float *>(c->d_stats + 4),
+                                    c->d_counters, c->mg.on ? c->mg.d_flags : nullptr);
+    SPHB_CUDA(cudaMemcpyAsync(h, c->d_stats, sizeof(StatsBlock), cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    decode_stats(c, h, out);
     return SPHB_OK;
 }
 

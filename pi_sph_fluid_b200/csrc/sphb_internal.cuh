@@ -43,6 +43,32 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 
 constexpr uint32_t kTrashKey = 0xffffffffu;   // build key of a slot that is dropped by the sort
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// The kernels of a step form one chain on one stream.  Each of them lets its successor's CTAs be
+// scheduled as soon as all of its own CTAs have started (pdl_trigger, first instruction) and waits for
+// its predecessor's completion and memory (pdl_wait) before it touches global memory, so launch
+// latency, CTA ramp-up and shared-memory set-up of kernel n+1 overlap the tail of kernel n.  Waiting
+// CTAs only ever occupy resources the predecessor no longer needs (all its CTAs are resident by then).
+// SPHB_NO_PDL=1 in the environment launches the same kernels plainly (the wait is then a no-op).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();      // sphb_api.cu
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(cudaStream_t st, dim3 grid, dim3 block, void (*kern)(KArgs...), Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at = {};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<Args &&>(args)...);
+}
+
 // Particle count of a launch: `n` sizes the grid (an upper bound when `dev` is set); the kernels
 // use *dev when it is non-null (multi-GPU slabs: counts change on the device every step).
 struct Count {
@@ -133,6 +159,21 @@ struct DeviceCounters {        // lives in HBM, read back by sphb_get_stats
     unsigned long long pair_accepted;
 };
 
+// Per-step statistics gathered by the force pass itself (sphb_step_stats): the 128-byte block of
+// sphb_get_stats (4 doubles | 16 words) is accumulated in HBM by one set of atomics per CTA, and the
+// last CTA to finish stores it, followed by a sequence word, into mapped pinned host memory — the
+// host polls that word, so reading a step's statistics costs no further API call.
+struct StepStats {
+    unsigned long long *block = nullptr;   // device: 16 x 8 bytes (zeroed by the density pass of the step)
+    const DeviceCounters *ctr = nullptr;
+    const unsigned int *flags = nullptr;   // slabs: [0] lost, [1] overflow
+    const uint32_t *id = nullptr;          // original index per sorted slot
+    uint32_t last_id = 0xffffffffu;        // :657-659 as written reports the LAST particle's error
+    unsigned int *done = nullptr;          // CTAs that have finished (left at zero by the last one)
+    unsigned long long *host = nullptr;    // mapped pinned: [0..15] the block, [16] sequence word
+    unsigned long long seq = 0;
+};
+
 // Multi-GPU slab state of one rank (sphb_mg.cu)
 struct MgState {
     bool on = false;
@@ -174,7 +215,10 @@ struct sphb_ctx {
     size_t pinned_bytes = 0;
     float2 *d_pixels = nullptr;           // pixel-centre pseudo-particles (:570-577)
     unsigned char *d_frame = nullptr;     // 1 KiB SSD1306 frame
-    double *d_stats = nullptr;            // 4 doubles + 4 words
+    double *d_stats = nullptr;            // 4 doubles + 16 words
+    unsigned int *d_stats_done = nullptr; // StepStats::done
+    unsigned long long *h_stats = nullptr;   // StepStats::host (mapped pinned, 17 words)
+    unsigned long long stats_seq = 0;
     void *d_l2_scratch = nullptr;         // sphb_flush_l2
     int l2_flush_value = 0;
     bool boundary_ready = false;
@@ -219,10 +263,11 @@ int launch_cell_ids(cudaStream_t st, const Consts &k, const ParticleSet &ps, int
 // ---- kernel launchers (kernels_pair.cu) ----------------------------------------------------
 int launch_pseudomass(cudaStream_t st, const Consts &k, ParticleSet &boundary);
 int launch_density(cudaStream_t st, const Consts &k, ParticleSet &fluid, const ParticleSet &boundary,
-                   DeviceCounters *ctr, bool count_pairs, bool allow_stage = true);
+                   DeviceCounters *ctr, bool count_pairs, bool allow_stage = true,
+                   unsigned long long *stats_zero = nullptr);
 int launch_force(cudaStream_t st, const Consts &k, ParticleSet &fluid, const ParticleSet &boundary,
                  float gx, float gy, const float2 *g_dev, bool kick2, DeviceCounters *ctr,
-                 bool allow_stage = true);
+                 bool allow_stage = true, const StepStats *stats = nullptr);
 int launch_neighbor_lists(cudaStream_t st, const Consts &k, const ParticleSet &a, const ParticleSet &b,
                           bool same, int cap, int *counts, int *lists, unsigned int *overflow);
 
@@ -239,7 +284,7 @@ int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_ma
 int ensure_stage(sphb_ctx *c, size_t bytes);
 int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk = nullptr);
 int step_phase_a(sphb_ctx *c, bool advect);
-int step_phase_b(sphb_ctx *c, float gx, float gy, bool kick2);
+int step_phase_b(sphb_ctx *c, float gx, float gy, bool kick2, const StepStats *ss = nullptr);
 int free_set_public(ParticleSet &ps);
 
 // sphb_mg.cu

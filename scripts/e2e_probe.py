@@ -24,3 +24,6 @@ timeit("step(1) + stats", lambda: (sim.step(1, 0.0, -9.81), sim.stats()))
 timeit("stats only", lambda: sim.stats())
 timeit("synchronize only", lambda: sim.synchronize())
 timeit("step(10) + stats", lambda: (sim.step(10, 0.0, -9.81), sim.stats()))
+timeit("step_stats(1)", lambda: sim.step_stats(g))
+g10 = np.tile(g, (10, 1))
+timeit("step_stats(10)", lambda: sim.step_stats(g10))

@@ -119,11 +119,8 @@ void emu_compute_accel(const sphb_params *prm, sphb_particle *f, int n, const sp
             const float dx = f_sub(f[i].x, f[j].x), dy = f_sub(f[i].y, f[j].y);
             const float d2 = dist2(dx, dy);
             if (within_support(k, d2) && j != i) {
-                float a3;
-                const float w = W_fast(k, d2, a3);
                 const float xu = dx * (f[i].u - f[j].u) + dy * (f[i].v - f[j].v);
-                const float temp = pair_temp(k, w, d2, xu, prr[i] + prr[j], 0.5f * (f[i].rho + f[j].rho));
-                const float tg = f[j].m * temp * grad_factor(k, d2, a3);
+                const float tg = f[j].m * force_pair(k, d2, xu, prr[i] + prr[j], f[i].rho + f[j].rho);
                 sx += tg * dx;
                 sy += tg * dy;
             }
@@ -133,17 +130,14 @@ void emu_compute_accel(const sphb_params *prm, sphb_particle *f, int n, const sp
                 const float dx = f_sub(f[i].x, b[j].x), dy = f_sub(f[i].y, b[j].y);
                 const float d2 = dist2(dx, dy);
                 if (within_support(k, d2)) {
-                    float a3;
-                    const float w = W_fast(k, d2, a3);
                     const float xu = dx * (f[i].u - b[j].u) + dy * (f[i].v - b[j].v);
-                    const float temp = pair_temp(k, w, d2, xu, prr[i], f[i].rho);
-                    const float tg = b[j].m * temp * grad_factor(k, d2, a3);
+                    const float tg = b[j].m * force_pair(k, d2, xu, prr[i], f[i].rho + f[i].rho);
                     bx += tg * dx;
                     by += tg * dy;
                 }
             });
-        du[i] = (gx - sx) - bx;
-        dv[i] = (gy - sy) - by;
+        du[i] = (gx - k.grad_c * sx) - k.grad_c * bx;
+        dv[i] = (gy - k.grad_c * sy) - k.grad_c * by;
     }
 }
 

@@ -331,6 +331,52 @@ def test_edge_sparse_scene_uses_unstaged_tiles(oracle_built, lib_built):
     sim.close()
 
 
+def test_step_stats_equals_step_then_get_stats(lib_built, golden075):
+    """sphb_step_stats (statistics reduced inside the force pass, delivered through mapped host memory)
+    against sphb_step_trace + sphb_get_stats on a second context: same state bit for bit, maxima and
+    minima identical, sums to double rounding (the atomics' order differs)."""
+    g = golden075
+    trace = np.asarray([[0.3 * np.sin(0.1 * i), -9.81 + 0.2 * np.cos(0.07 * i)] for i in range(37)], np.float32)
+    a = run_gpu(lib_built, 0.075, g["fluid_2000"], g["boundary_init"])
+    b = run_gpu(lib_built, 0.075, g["fluid_2000"], g["boundary_init"])
+    a.compute_accel(*G); b.compute_accel(*G)
+    for lo, hi in ((0, 1), (1, 2), (2, 20), (20, 37)):
+        sa = a.step_stats(trace[lo:hi])
+        b.step_trace(trace[lo:hi])
+        sb = b.stats()
+        for key in ("max_speed", "max_rho", "min_rho", "max_rho_err", "last_rho_err_ref", "n_fluid", "n_boundary",
+                    "n_escaped", "max_cell_count", "steps", "n_lost", "n_overflow"):
+            assert sa[key] == sb[key], (key, sa[key], sb[key])
+        for key in ("mass", "mom_x", "mom_y", "kinetic"):
+            assert sa[key] == pytest.approx(sb[key], rel=1e-12, abs=1e-12), key
+    fa, dua, dva = a.download(); fb, dub, dvb = b.download()
+    for fld in FIELDS:
+        assert same_bits(fa[fld], fb[fld]), fld
+    assert same_bits(dua, dub) and same_bits(dva, dvb)
+    with pytest.raises(Exception):
+        a.step_stats(np.zeros((0, 2), np.float32))
+    a.close(); b.close()
+
+
+def test_step_stats_large_scene(lib_built):
+    """Many CTAs (R = 0.01: ~15k particles, >100 chunks): the last-CTA delivery and the per-CTA atomics."""
+    prm = lib_built.default_params(0.01)
+    fluid, boundary = lib_built.scene_drop(prm), lib_built.scene_boundary(prm)
+    g1 = np.asarray([G], np.float32)
+    with lib_built.Simulation(prm) as a, lib_built.Simulation(prm) as b:
+        for s in (a, b):
+            s.upload(fluid, boundary); s.init_boundary(); s.compute_accel(*G)
+        for it in range(25):
+            sa = a.step_stats(g1)
+            b.step_trace(g1)
+            sb = b.stats()
+            assert sa["max_speed"] == sb["max_speed"] and sa["max_rho"] == sb["max_rho"] and sa["min_rho"] == sb["min_rho"]
+            assert sa["last_rho_err_ref"] == sb["last_rho_err_ref"] and sa["steps"] == sb["steps"] == it + 1
+            assert sa["mass"] == pytest.approx(sb["mass"], rel=1e-13)
+            assert sa["kinetic"] == pytest.approx(sb["kinetic"], rel=1e-11)
+            assert sa["mom_y"] == pytest.approx(sb["mom_y"], rel=1e-11)
+
+
 def test_edge_escaped_particles_are_clamped_and_counted(lib_built, golden075):
     fluid = golden075["fluid_init"].copy()
     fluid["x"][5] = -3.0; fluid["y"][9] = 7.5; fluid["x"][11] = 4.3
