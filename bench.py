@@ -74,6 +74,51 @@ def read_peaks():
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
+def read_traffic(workload: str) -> dict:
+    """Per-kernel DRAM bytes per launch from the committed `ncu --set full` capture of this workload
+    (profiles/r01b_traffic.json, written by scripts/ncu_traffic.py); {} when there is none."""
+    p = ROOT / "profiles" / "r01b_traffic.json"
+    try:
+        return json.loads(p.read_text()).get(workload, {})
+    except (OSError, ValueError):
+        return {}
+
+
+def make_roofline(workload, n, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_max_mhz, peak_src, sm_count, suffix=""):
+    """The roofline object of the JSON line, for the DOMINANT kernel of the step (the pair kernel with
+    the longer average launch, CUDA events on the library's stream).  `achieved` = algorithmic bytes of
+    one launch (SURVEY.md 8d per-particle figure x particles) / that duration.  Both pair kernels are
+    FP32-issue-bound, so the flop-side figures and ncu's issue-slot utilisation are listed next to it."""
+    traffic = read_traffic(workload)
+    ms = {"force": force_ms, "density": dens_ms}
+    dom = "density" if dens_ms >= force_ms else "force"
+    achieved = ALGO_BYTES[dom] * n / (ms[dom] * 1e-3) / 1e9
+    fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    flops = {"force": (6 * cand + 44 * acc) * n, "density": (6 * cand + 13 * acc) * n}
+    tf = {k: flops[k] / (ms[k] * 1e-3) / 1e12 for k in ms}
+    for name, d in kern.items():
+        t = traffic.get(name)
+        if t:
+            d["ncu_dram_bytes_per_launch"] = t["traffic_bytes"]
+            d["ncu_issue_active_pct"] = t["issue_active_pct"]
+    t = traffic.get(dom)
+    return {
+        "kernel": f"k_{dom}{suffix}", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
+        "frac": round(achieved / hbm_peak, 5), "traffic": t["traffic_bytes"] if t else None,
+        "traffic_source": "profiles/r01b_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if t else None,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * n,
+        "note": "k_density and k_force are FP32-issue-bound, not HBM-bound (SURVEY.md §8d): see fp32 and the "
+                "ncu issue-slot utilisation per kernel; DRAM traffic above the algorithmic bytes is the "
+                "neighbour lists k_density hands to k_force",
+        "fp32": {"force_TFLOPs": round(tf["force"], 3), "density_TFLOPs": round(tf["density"], 3),
+                 "peak_TFLOPs": round(fp32_peak, 1), "peak_def": f"{sm_count} SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz",
+                 "force_frac": round(tf["force"] / fp32_peak, 4), "density_frac": round(tf["density"] / fp32_peak, 4),
+                 "pairs_per_particle": {"candidates": round(cand, 2), "accepted": round(acc, 2)}},
+        "kernels": kern,
+    }
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -285,24 +330,8 @@ def run_gpu(args, spec, rank, world):
             kern[name]["algo_GBps"] = round(ALGO_BYTES[name] * n / (ms * 1e-3) / 1e9, 2)
     force_ms = prof["force"]["ms"] / max(1, prof["force"]["launches"])
     dens_ms = prof["density"]["ms"] / max(1, prof["density"]["launches"])
-    achieved = ALGO_BYTES["force"] * n / (force_ms * 1e-3) / 1e9
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
-    force_flops = (6 * cand + 44 * acc) * n
-    dens_flops = (6 * cand + 13 * acc) * n
-    roofline = {
-        "kernel": "k_force", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-        "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_particle": ALGO_BYTES["force"],
-        "note": "k_force and k_density are FP32-issue-bound, not HBM-bound (SURVEY.md §8d); see fp32",
-        "fp32": {"force_TFLOPs": round(force_flops / (force_ms * 1e-3) / 1e12, 3),
-                 "density_TFLOPs": round(dens_flops / (dens_ms * 1e-3) / 1e12, 3),
-                 "peak_TFLOPs": round(fp32_peak, 1), "peak_def": f"{sm_count} SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz",
-                 "force_frac": round(force_flops / (force_ms * 1e-3) / 1e12 / fp32_peak, 4),
-                 "density_frac": round(dens_flops / (dens_ms * 1e-3) / 1e12 / fp32_peak, 4),
-                 "pairs_per_particle": {"candidates": round(cand, 2), "accepted": round(acc, 2)}},
-        "kernels": kern,
-    }
+    roofline = make_roofline(args.workload, n, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_max_mhz, peak_src, sm_count)
 
     if args.no_e2e:
         sim.close()
@@ -459,22 +488,10 @@ def run_gpu_slabs(args, spec, rank, world):
                 kern[name]["algo_GBps"] = round(ALGO_BYTES[name] * n_local / (ms * 1e-3) / 1e9, 2)
     force_ms = prof["force"]["ms"] / max(1, prof["force"]["launches"])
     dens_ms = prof["density"]["ms"] / max(1, prof["density"]["launches"])
-    achieved = ALGO_BYTES["force"] * n_local / (force_ms * 1e-3) / 1e9
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
-    roofline = {
-        "kernel": "k_force (rank 0)", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-        "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_particle": ALGO_BYTES["force"],
-        "note": "k_force and k_density are FP32-issue-bound, not HBM-bound (SURVEY.md §8d); see fp32",
-        "fp32": {"force_TFLOPs": round((6 * cand + 44 * acc) * n_local / (force_ms * 1e-3) / 1e12, 3),
-                 "density_TFLOPs": round((6 * cand + 13 * acc) * n_local / (dens_ms * 1e-3) / 1e12, 3),
-                 "peak_TFLOPs": round(fp32_peak, 1),
-                 "force_frac": round((6 * cand + 44 * acc) * n_local / (force_ms * 1e-3) / 1e12 / fp32_peak, 4),
-                 "density_frac": round((6 * cand + 13 * acc) * n_local / (dens_ms * 1e-3) / 1e12 / fp32_peak, 4),
-                 "pairs_per_particle": {"candidates": round(cand, 2), "accepted": round(acc, 2)}},
-        "kernels": kern,
-    }
+    # per-GPU load is the 8M-particle dam-break slab: the committed ncu capture of dam8m is the matching one
+    roofline = make_roofline("dam8m", n_local, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_max_mhz, peak_src,
+                             sm_count, suffix=" (rank 0)")
 
     # ---- e2e: host buffers -> C ABI -> host buffers on every rank
     pcap = info["particle_capacity"]
@@ -550,7 +567,8 @@ def main():
     if args.warmup is None:
         args.warmup = 20 if world == 1 else 10
     # N = 1: BASELINE configs[1].  N > 1: dam break with 8M particles per GPU (N = 8 is configs[3], 64M)
-    spec = workload_spec(args.workload or ("drop256k" if world == 1 else f"dam{8 * world}m"))
+    args.workload = args.workload or ("drop256k" if world == 1 else f"dam{8 * world}m")
+    spec = workload_spec(args.workload)
 
     if args.impl == "reference":
         if rank != 0:
