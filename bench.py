@@ -57,6 +57,12 @@ def workload_spec(name: str):
         return dict(name="drop_R0.075_269_fluid (BASELINE configs[0])", R=0.075, scene="drop", ref_tag=None)
     if name == "dam4m":
         return dict(name="dam_break_R0.0005_4M (BASELINE configs[2])", R=0.0005, scene="dam", block=(2.0, 0.5), ref_tag=None)
+    if name == "slosh16m":
+        # BASELINE configs[4]: tank filled to y = 1 m, R = 5e-4 -> 16M particles, gravity from a synthetic
+        # MPU6050 trace (+-20 degrees, one period per 2000 steps, samples held 50 steps)
+        R = 5e-4
+        return dict(name="slosh_tank_filled_to_1m_R5e-04_16M_tilt20deg (BASELINE configs[4])", R=R, scene="tank",
+                    box=(2 * R, 4.0 - 2 * R, 2 * R, 1.0), tilt=(20.0, 2000, 50), ref_tag=None)
     if name.startswith("dam") and name.endswith("m"):
         # dam break, block x in [2R,2) x y in [2R,1): 2 m^2 -> R = sqrt(2 / N).  dam64m = BASELINE configs[3]
         n = float(name[3:-1]) * 1e6
@@ -169,6 +175,8 @@ def build_scene(pkg, spec, deterministic=True, device=0):
     prm = pkg.default_params(spec["R"], deterministic=deterministic, device=device)
     if spec["scene"] == "drop":
         fluid = pkg.scene_drop(prm)
+    elif "box" in spec:
+        fluid = pkg.scene_block(prm, *spec["box"])
     else:
         x1, y1 = spec["block"]
         fluid = pkg.scene_block(prm, 2 * spec["R"], x1, 2 * spec["R"], y1)     # 2R off the walls (DESIGN.md "Scenes")
@@ -406,8 +414,11 @@ def run_gpu_slabs(args, spec, rank, world):
     torch.cuda.set_device(dev)
     R = spec["R"]
     prm = pkg.default_params(R, deterministic=not args.nondeterministic, device=dev)
-    x1, y1 = spec["block"]
-    box = (2 * R, x1, 2 * R, y1)
+    if "box" in spec:
+        box = spec["box"]
+    else:
+        x1, y1 = spec["block"]
+        box = (2 * R, x1, 2 * R, y1)
     hist = pkg.scene_block_column_hist(prm, *box)
     cuts = pkg.plan_cuts(hist, world)
     n_total = int(hist.sum())
@@ -435,13 +446,26 @@ def run_gpu_slabs(args, spec, rank, world):
     fl_host[:] = part
     sim.upload(fl_host, boundary, id_base=base)
     sim.init_boundary()
-    sim.compute_accel(*G)
+    # gravity: constant, or (slosh) one sample per step from the synthetic accelerometer trace; the trace
+    # position carries on across warm-up, timed steps and the per-kernel pass
+    tilt = spec.get("tilt")
+    g_trace = pkg.gravity_trace_tilt(prm, tilt[0], tilt[1], tilt[2], W + 100 + 2 * K + 64) if tilt else None
+    g_pos = [0]
+
+    def advance(s_, nsteps):
+        if g_trace is None:
+            s_.step(nsteps, *G)
+        else:
+            s_.step_trace(g_trace[g_pos[0]:g_pos[0] + nsteps])
+            g_pos[0] += nsteps
+    g0 = tuple(float(v) for v in g_trace[0]) if tilt else G
+    sim.compute_accel(*g0)
     clocks = ClockSampler(dev)           # from the warm-up on: the timed region alone may be shorter than a sample
     clocks.start()
-    sim.step(W, *G)
+    advance(sim, W)
     sim.synchronize()
     clocks.wait_first()
-    sim.step(100, *G)
+    advance(sim, 100)
     sim.synchronize()
 
     def barrier():
@@ -459,7 +483,7 @@ def run_gpu_slabs(args, spec, rank, world):
     barrier()
     t_wall0 = time.perf_counter()
     a.record(stream)
-    sim.step(K, *G)
+    advance(sim, K)
     b.record(stream)
     sim.synchronize()
     barrier()
@@ -472,7 +496,7 @@ def run_gpu_slabs(args, spec, rank, world):
     # ---- per-kernel CUDA-event times on this rank (separate pass)
     cand, acc = sim.pair_stats()
     sim.profile(1); sim.profile_read(reset=True)
-    sim.step(min(K, 20), *G)
+    advance(sim, min(K, 20))
     prof = sim.profile_read(reset=True)
     sim.profile(0)
     st = sim.allreduce_stats()
@@ -503,15 +527,15 @@ def run_gpu_slabs(args, spec, rank, world):
     ident2 = [pkg.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ident2, src=0)
     sim2.connect_nccl(ident2[0])
-    sim2.upload(fl_host, boundary, id_base=base); sim2.init_boundary(); sim2.compute_accel(*G); sim2.step(W, *G); sim2.synchronize()
-    trace = np.tile(np.asarray([G], np.float32), (K, 1))
+    sim2.upload(fl_host, boundary, id_base=base); sim2.init_boundary(); sim2.compute_accel(*g0); sim2.step(W, *g0); sim2.synchronize()
+    trace = g_trace[:K] if tilt else np.tile(np.asarray([G], np.float32), (K, 1))
     runs, last, n_out = [], None, 0
     for _rep in range(3):
         barrier()
         t0 = time.perf_counter()
         sim2.upload(fl_host, boundary, id_base=base)
         sim2.init_boundary()
-        sim2.compute_accel(*G)
+        sim2.compute_accel(*g0)
         for s_ in range(K):
             last = sim2.step_stats(trace[s_:s_ + 1])
         n_out = sim2.download_into(out_host, ids_host, du_host, dv_host)
@@ -531,13 +555,15 @@ def run_gpu_slabs(args, spec, rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic (dam-break block on the reference's lattice idiom; not a reference scene)",
+        "dtype": "f32", "data": ("synthetic (filled tank on the reference's lattice idiom, gravity from a synthetic MPU6050 tilt trace mapped as pi_sph_fluid.c:439-440; not a reference scene)"
+                                 if tilt else "synthetic (dam-break block on the reference's lattice idiom; not a reference scene)"),
         "config": {"workload": spec["name"], "n_fluid": n_total, "n_boundary": int(len(boundary)), "R": R,
                    "particles_per_gpu": [int(hist[int(cuts[r]):int(cuts[r + 1])].sum()) for r in range(world)],
                    "parallelism": f"x-slabs of cell columns, cuts at particle-count quantiles {[int(c) for c in cuts]}, "
                                   "2 ghost columns, one halo+migration message per neighbour per step over NCCL",
                    "halo_message_bytes": info["message_bytes"], "deterministic_order": not args.nondeterministic,
-                   "l2": "not flushed: per-GPU state (~100 B x 8M particles) is far larger than the 126 MB L2",
+                   "gravity": (f"tilt trace: +-{tilt[0]} deg, period {tilt[1]} steps, sample held {tilt[2]} steps, one (gx, gy) per step" if tilt else "constant (0, -9.81)"),
+                   "l2": f"not flushed: per-GPU state (~100 B x {n_total / world / 1e6:.0f}M particles) is far larger than the 126 MB L2",
                    "timing": "CUDA events on the library stream around the K steps, barrier + synchronize both sides; max over ranks",
                    "wall_s_timed_region": round(t_wall, 4),
                    "merged_stats": {k2: st[k2] for k2 in ("n_fluid", "n_lost", "n_overflow", "n_escaped", "max_speed", "max_rho_err")},
@@ -595,6 +621,8 @@ def main():
                          "(use --impl reference for the CPU arm)")
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+    if world == 1 and "tilt" in spec:
+        raise SystemExit("bench.py: the sloshing workload is a slab (multi-GPU) bench line: launch it under torchrun with --gpus 2|4|8")
     line = run_gpu_slabs(args, spec, rank, world) if world > 1 else run_gpu(args, spec, rank, world)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
