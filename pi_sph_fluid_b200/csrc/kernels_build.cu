@@ -249,41 +249,25 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
             if (lane == 0) st_volatile_u64(&tile_state[0], pack_state(epoch, kFlagPrefix, aggregate));
         } else {
             if (lane == 0) st_volatile_u64(&tile_state[tile], pack_state(epoch, kFlagAggregate, aggregate));
-            // Look-back, kLookGroups x 32 predecessors per round trip: when every tile of the grid is
-            // resident at once (one wave), all aggregates appear together and hardly any prefix yet, so
-            // a tile walks most of the way back; the loads of one round are issued together so that
-            // walk costs one memory latency per kLookGroups x 32 tiles instead of one per 32.
-            constexpr int kLookGroups = 8;
             int look = (int)tile - 1;
-            bool found = false;
-            while (!found) {
-                unsigned long long stv[kLookGroups];
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long st;
+                bool invalid;
+                do {
+                    st = idx >= 0 ? ld_volatile_u64(&tile_state[idx]) : pack_state(epoch, kFlagPrefix, 0u);
+                    const unsigned int hi = (unsigned int)(st >> 32);
+                    invalid = ((hi >> 2) != epoch) || ((hi & 3u) == 0u);
+                } while (__any_sync(0xffffffffu, invalid));
+                const bool is_prefix = (((unsigned int)(st >> 32)) & 3u) == kFlagPrefix;
+                const unsigned int mask = __ballot_sync(0xffffffffu, is_prefix);
+                const int first = mask ? (__ffs(mask) - 1) : 32;
+                uint32_t contrib = (lane <= first) ? (uint32_t)st : 0u;
 #pragma unroll
-                for (int j = 0; j < kLookGroups; j++) {
-                    const int idx = look - 32 * j - lane;
-                    stv[j] = idx >= 0 ? ld_volatile_u64(&tile_state[idx]) : pack_state(epoch, kFlagPrefix, 0u);
-                }
-#pragma unroll
-                for (int j = 0; j < kLookGroups; j++) {
-                    if (found) break;
-                    const int idx = look - 32 * j - lane;
-                    unsigned long long st = stv[j];
-                    while (true) {
-                        const unsigned int hi = (unsigned int)(st >> 32);
-                        const bool invalid = ((hi >> 2) != epoch) || ((hi & 3u) == 0u);
-                        if (!__any_sync(0xffffffffu, invalid)) break;
-                        st = idx >= 0 ? ld_volatile_u64(&tile_state[idx]) : pack_state(epoch, kFlagPrefix, 0u);
-                    }
-                    const bool is_prefix = (((unsigned int)(st >> 32)) & 3u) == kFlagPrefix;
-                    const unsigned int mask = __ballot_sync(0xffffffffu, is_prefix);
-                    const int first = mask ? (__ffs(mask) - 1) : 32;
-                    uint32_t contrib = (lane <= first) ? (uint32_t)st : 0u;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                    excl += contrib;
-                    found = mask != 0u;
-                }
-                look -= 32 * kLookGroups;
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                excl += contrib;
+                if (mask) break;
+                look -= 32;
             }
             if (lane == 0) st_volatile_u64(&tile_state[tile], pack_state(epoch, kFlagPrefix, excl + aggregate));
         }
