@@ -456,6 +456,46 @@ def test_full_size_config2_properties(oracle_built, lib_built):
     sim.close(); sim2.close()
 
 
+def test_full_size_config3_dam_break_4m(oracle_built, lib_built):
+    """BASELINE.json configs[2] at FULL size: 2-D dam break, block x in [2R, 2) x y in [2R, 0.5) at
+    R = 5e-4 -> 3,995,001 fluid + 24,004 boundary particles (artificial-pressure term on, as always
+    in the reference, :325).  The oracle needs ~1 s per pass here, so one whole pass and five
+    leapfrog steps are compared directly; then three in-process slabs against the single GPU."""
+    pkg = lib_built
+    R = 0.0005
+    prm = pkg.default_params(R)
+    fluid, boundary = pkg.scene_block(prm, 2 * R, 2.0, 2 * R, 0.5), pkg.scene_boundary(prm)
+    assert len(fluid) == 3995001 and len(boundary) == 24004
+    sim = pkg.Simulation(prm)
+    sim.upload(fluid, boundary); sim.init_boundary(); sim.compute_accel(*G)
+    f, du, dv = sim.download()
+    o, of, ob, gf, gb, odu, odv = oracle_state(oracle_built, R, "chain", fluid, boundary)
+    assert np.array_equal(sim.cell_ids(), o.cell_ids(gf, of))                         # exact
+    assert same_bits(sim.download_boundary()["m"], ob["m"])                          # psi bit-for-bit
+    assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])             # bit-for-bit
+    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    sim.step(5, *G)
+    o.step(of, ob, gf, gb, odu, odv, 5, *G)
+    f5, du5, dv5 = sim.download()
+    st = sim.stats()
+    assert np.abs(f5["x"] - of["x"]).max() < 1e-6 and np.abs(f5["y"] - of["y"]).max() < 1e-6
+    # positions may differ by an ulp after five steps, which moves rho by ~1e-6 (and p by 7x that
+    # times B): the north-star tolerance, not the one-pass one, applies from here on
+    assert (np.abs(f5["rho"].astype("f8") - of["rho"]) / of["rho"]).max() < 1e-4
+    assert same_bits(f5["m"], fluid["m"])                                            # permutation intact
+    assert st["mass"] == pytest.approx(fluid["m"].astype("f8").sum(), rel=1e-12)
+    assert st["n_escaped"] == 0 and st["n_fluid"] == len(fluid)
+    sim.close()
+    # three slabs in this process (cuts at the particle-count quantiles): bit-identical to the above
+    cuts = pkg.plan_cuts(pkg.column_histogram(prm, fluid), 3)
+    with pkg.SlabGroup(prm, cuts) as grp:
+        grp.upload(fluid, boundary); grp.init_boundary(); grp.compute_accel(*G); grp.step(5, *G)
+        g5, gdu, gdv, owner = grp.download()
+        gst = grp.stats()
+    assert all(same_bits(f5[k], g5[k]) for k in FIELDS) and same_bits(du5, gdu) and same_bits(dv5, gdv)
+    assert gst["n_lost"] == 0 and gst["n_overflow"] == 0 and gst["n_fluid"] == len(fluid)
+
+
 def test_dam_break_scene_steps(oracle_built, lib_built):
     """Builder-defined dam break (SURVEY.md §8d cfg3 geometry, reduced R; the block starts 2R off
     the walls — at R the single-layer wall, psi = 4.2 m, gives rho = 1707 and p = 9e8 Pa at t = 0
