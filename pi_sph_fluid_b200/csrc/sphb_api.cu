@@ -39,7 +39,7 @@ static void free_set(ParticleSet &ps)
     }
     cudaFree(ps.acc); cudaFree(ps.rho_prr); cudaFree(ps.p); cudaFree(ps.key); cudaFree(ps.rank);
     cudaFree(ps.ids_tmp); cudaFree(ps.cell_count); cudaFree(ps.cell_start); cudaFree(ps.cellkey);
-    cudaFree(ps.nbr_list); cudaFree(ps.nbr_count); cudaFree(ps.nbr_rows); cudaFree(ps.chunk_queue);
+    cudaFree(ps.nbr_list); cudaFree(ps.nbr_count); cudaFree(ps.chunk_rec); cudaFree(ps.chunk_queue);
     ps = ParticleSet();
 }
 
@@ -77,7 +77,7 @@ int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_ma
         const size_t ctas = ((size_t)n + kPairThreads - 1) / kPairThreads + 1;
         SPHB_CUDA(dmalloc(&ps.nbr_list, ctas * kListCap * kPairThreads));
         SPHB_CUDA(dmalloc(&ps.nbr_count, ctas * kPairThreads));
-        SPHB_CUDA(dmalloc(&ps.nbr_rows, ctas));
+        SPHB_CUDA(dmalloc(&ps.chunk_rec, ctas * (size_t)kChunkRecWords));
         SPHB_CUDA(dmalloc(&ps.chunk_queue, 2));
         SPHB_CUDA(cudaMemset(ps.chunk_queue, 0, 2 * sizeof(unsigned long long)));
     }

@@ -34,6 +34,7 @@ constexpr int kStreamThreads = 256;   // advect/bin, reorder, gather/scatter ker
 #define SPHB_MINB_F 8
 #endif
 constexpr int kPairThreads = SPHB_PT;        // density / force CTAs: one thread per particle
+constexpr int kChunkRecWords = 16;           // the record k_density leaves per chunk for k_force (64 bytes)
 constexpr int kListCap = SPHB_LIST_CAP;      // per-thread accepted list entries (u16 tile offsets) before a flush
 constexpr int kTileCap = SPHB_TILE_CAP;      // staged neighbourhood entries per CTA (x 8 B must stay < 64 KiB)
 constexpr int kWinCap = SPHB_WIN_CAP;        // staged cell_start words per neighbour row of a chunk (multiple of 4)
@@ -129,7 +130,9 @@ struct ParticleSet {
     // accepted-neighbour lists handed from the density pass to the force pass of the same step
     unsigned short *nbr_list = nullptr;       // [CTA][entry < kListCap][thread] tile byte offsets
     unsigned short *nbr_count = nullptr;      // per sorted slot; 0xffff = search again
-    unsigned int *nbr_rows = nullptr;         // per CTA: rows of its block in use
+    unsigned int *chunk_rec = nullptr;        // per chunk, kChunkRecWords words: [S0 S1 S2 | n0 n1 n2 | w0 w1 w2 |
+                                              //   wn0 wn1 wn2 | flags (1 whole-chunk plan valid, 2 wall near,
+                                              //   4 cell_start windows staged) | rows of its list block in use]
     bool lists_valid = false;
     // chunk tickets of the density [0] and force [1] kernels (kernels_pair.cu: ChunkQueue)
     unsigned long long *chunk_queue = nullptr;

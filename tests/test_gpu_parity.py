@@ -473,7 +473,17 @@ def test_full_size_config3_dam_break_4m(oracle_built, lib_built):
     assert np.array_equal(sim.cell_ids(), o.cell_ids(gf, of))                         # exact
     assert same_bits(sim.download_boundary()["m"], ob["m"])                          # psi bit-for-bit
     assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])             # bit-for-bit
-    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    # Acceleration: an interior particle's a = g - (a cancelling sum of ~20 artificial-pressure pair
+    # terms, :325), and the term size grows like 1/H: at this spacing the uncancelled half-sum at the
+    # free surface is max|a| ~ 1100 m/s^2 while the result is ~ G.  Rounding noise scales with the
+    # terms, not with the result, so the floor of the relative error is max(G, 0.1 max|a|) here
+    # (measured: 3.5e-3 m/s^2 absolute = 3.2e-6 of max|a|; 3.6e-4 of G).  At R >= 0.0024 the terms are
+    # <= 230 m/s^2 and the plain floor G of the other tests holds.
+    a_ref = np.hypot(odu.astype("f8"), odv)
+    floor = max(9.81, 0.1 * a_ref.max())
+    err = np.hypot(du.astype("f8") - odu, dv.astype("f8") - odv) / np.maximum(a_ref, floor)
+    assert err.max() < TOL_A
+    assert np.median(accel_err(du, dv, odu, odv)) < 1e-6
     sim.step(5, *G)
     o.step(of, ob, gf, gb, odu, odv, 5, *G)
     f5, du5, dv5 = sim.download()
