@@ -80,12 +80,18 @@ def read_peaks():
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_file():
+    """The newest committed ncu traffic summary (profiles/rNN*_traffic.json, scripts/ncu_traffic.py)."""
+    files = sorted((ROOT / "profiles").glob("r*_traffic.json"))
+    return files[-1] if files else None
+
+
 def read_traffic(workload: str) -> dict:
-    """Per-kernel DRAM bytes per launch from the committed `ncu --set full` capture of this workload
-    (profiles/r01b_traffic.json, written by scripts/ncu_traffic.py); {} when there is none."""
-    p = ROOT / "profiles" / "r01b_traffic.json"
+    """Per-kernel DRAM bytes per launch from the committed `ncu --set full` capture of this workload;
+    {} when there is none."""
+    p = traffic_file()
     try:
-        return json.loads(p.read_text()).get(workload, {})
+        return json.loads(p.read_text()).get(workload, {}) if p else {}
     except (OSError, ValueError):
         return {}
 
@@ -111,7 +117,7 @@ def make_roofline(workload, n, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_
     return {
         "kernel": f"k_{dom}{suffix}", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
         "frac": round(achieved / hbm_peak, 5), "traffic": t["traffic_bytes"] if t else None,
-        "traffic_source": "profiles/r01b_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if t else None,
+        "traffic_source": f"profiles/{traffic_file().name} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if t else None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * n,
         "note": "k_density and k_force are FP32-issue-bound, not HBM-bound (SURVEY.md §8d): see fp32 and the "
