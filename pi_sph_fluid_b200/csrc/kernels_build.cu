@@ -183,21 +183,16 @@ __device__ __forceinline__ unsigned long long pack_state(unsigned int epoch, uns
     return ((unsigned long long)((epoch << 2) | flag) << 32) | value;
 }
 
-// One tile = THREADS * ITEMS counters.  Tile ids are handed out by an atomic so a tile only ever
+// One tile = kScanTile counters.  Tile ids are handed out by an atomic so a tile only ever
 // waits on tiles that already started (forward progress without relying on block order).
-// Two shapes: 256 x 8 for small grids (many CTAs to pull the counters in), 1024 x 16 for grids of
-// millions of cells — there every tile of the small shape is resident at once, all aggregates appear
-// together and hardly any prefix yet, so the look-back of tile t walks ~t/64 rounds of one memory
-// latency each (31 us at 2.4M cells); eight times fewer tiles make that walk three rounds.
-template <int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(kScanThreads)
 k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
        unsigned long long *__restrict__ tile_state, unsigned long long *__restrict__ tile_counter,
        const unsigned long long counter_base, const unsigned int epoch, const int n_tiles,
        DeviceCounters *__restrict__ ctr, int *__restrict__ n_out)
 {
-    __shared__ uint32_t s_warp_sum[THREADS / 32];
-    __shared__ uint32_t s_warp_max[THREADS / 32];
+    __shared__ uint32_t s_warp_sum[kScanThreads / 32];
+    __shared__ uint32_t s_warp_max[kScanThreads / 32];
     __shared__ uint32_t s_tile, s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
@@ -205,22 +200,21 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
     if (tid == 0) s_tile = (uint32_t)(atomicAdd(tile_counter, 1ULL) - counter_base);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const long long base = (long long)tile * (THREADS * ITEMS) + (long long)tid * ITEMS;
+    const long long base = (long long)tile * kScanTile + (long long)tid * kScanItems;
 
-    uint32_t v[ITEMS];
-    if (base + ITEMS <= n) {
-#pragma unroll
-        for (int q = 0; q < ITEMS / 4; q++) {
-            const uint4 a = *reinterpret_cast<const uint4 *>(count + base + 4 * q);
-            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
-        }
+    uint32_t v[kScanItems];
+    if (base + kScanItems <= n) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(count + base);
+        const uint4 b = *reinterpret_cast<const uint4 *>(count + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++) v[i] = (base + i < n) ? count[base + i] : 0u;
+        for (int i = 0; i < kScanItems; i++) v[i] = (base + i < n) ? count[base + i] : 0u;
     }
     uint32_t tsum = 0, tmax = 0;
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
+    for (int i = 0; i < kScanItems; i++) {
         const uint32_t c = v[i];
         v[i] = tsum;                 // exclusive within the thread
         tsum += c;
@@ -243,7 +237,7 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
     __syncthreads();
     uint32_t warp_excl = 0, aggregate = 0;
 #pragma unroll
-    for (int w = 0; w < THREADS / 32; w++) {
+    for (int w = 0; w < kScanThreads / 32; w++) {
         const uint32_t ws = s_warp_sum[w];
         if (w < warp) warp_excl += ws;
         aggregate += ws;
@@ -281,7 +275,7 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
             s_prefix = excl;
             uint32_t m = 0;
 #pragma unroll
-            for (int w = 0; w < THREADS / 32; w++) m = s_warp_max[w] > m ? s_warp_max[w] : m;
+            for (int w = 0; w < kScanThreads / 32; w++) m = s_warp_max[w] > m ? s_warp_max[w] : m;
             if (m) atomicMax(&ctr->max_cell_count, m);
             if ((int)tile == n_tiles - 1) {
                 start[n] = excl + aggregate;
@@ -291,34 +285,26 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
     }
     __syncthreads();
     const uint32_t off = s_prefix + warp_excl + (incl - tsum);
-    if (base + ITEMS <= n) {
-#pragma unroll
-        for (int q = 0; q < ITEMS / 4; q++) {
-            *reinterpret_cast<uint4 *>(start + base + 4 * q) =
-                make_uint4(off + v[4 * q], off + v[4 * q + 1], off + v[4 * q + 2], off + v[4 * q + 3]);
-            *reinterpret_cast<uint4 *>(count + base + 4 * q) = make_uint4(0, 0, 0, 0);
-        }
+    if (base + kScanItems <= n) {
+        *reinterpret_cast<uint4 *>(start + base) = make_uint4(off + v[0], off + v[1], off + v[2], off + v[3]);
+        *reinterpret_cast<uint4 *>(start + base + 4) = make_uint4(off + v[4], off + v[5], off + v[6], off + v[7]);
+        *reinterpret_cast<uint4 *>(count + base) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(count + base + 4) = make_uint4(0, 0, 0, 0);
     } else {
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++)
+        for (int i = 0; i < kScanItems; i++)
             if (base + i < n) { start[base + i] = off + v[i]; count[base + i] = 0u; }
     }
 }
 
 int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc, DeviceCounters *ctr)
 {
-    const bool big = k.ncells >= kScanBigGrid;
-    const int tile = big ? 1024 * 16 : kScanTile;
-    const int n_tiles = (k.ncells + tile - 1) / tile;       // <= ScanState::n_tiles (sized for the small shape)
+    const int n_tiles = (k.ncells + kScanTile - 1) / kScanTile;
     sc.epoch = (sc.epoch + 1) & 0x3fffffffu;
     if (sc.epoch == 0) sc.epoch = 1;   // 0 is the memset state ("never written")
     const unsigned long long base = sc.launches;   // tiles handed out so far
-    if (big)
-        launch_pdl(st, n_tiles, 1024, k_scan<1024, 16>, ps.cell_count, ps.cell_start, k.ncells, sc.tile_state,
-                   sc.tile_counter, base, sc.epoch, n_tiles, ctr, ps.d_n_cur);
-    else
-        launch_pdl(st, n_tiles, kScanThreads, k_scan<kScanThreads, kScanItems>, ps.cell_count, ps.cell_start, k.ncells,
-                   sc.tile_state, sc.tile_counter, base, sc.epoch, n_tiles, ctr, ps.d_n_cur);
+    launch_pdl(st, n_tiles, kScanThreads, k_scan, ps.cell_count, ps.cell_start, k.ncells, sc.tile_state,
+               sc.tile_counter, base, sc.epoch, n_tiles, ctr, ps.d_n_cur);
     sc.launches += (unsigned long long)n_tiles;
     return 1;
 }

@@ -41,7 +41,6 @@ constexpr int kWinCap = SPHB_WIN_CAP;        // staged cell_start words per neig
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
-constexpr int kScanBigGrid = 1 << 20;        // cells from which the scan uses its 1024 x 16 tile shape
 
 constexpr uint32_t kTrashKey = 0xffffffffu;   // build key of a slot that is dropped by the sort
 
