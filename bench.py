@@ -192,6 +192,15 @@ def build_scene(pkg, spec, deterministic=True, device=0):
 
 # ------------------------------------------------------------------------------------------ CPU arm
 
+def host_cores() -> int:
+    """The host threads the CPU arm uses: every core this process may run on.  Asked for explicitly
+    (num_threads / omp_set_num_threads), because torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def run_reference(spec, steps: int, warmup: int, budget_s: float = 90.0):
     """Times the reference's own compiled operators (oracle/_ref, shipped -Ofast flags, OpenMP
     over all host cores) on the workload.  Returns dict or None if unavailable."""
@@ -207,11 +216,10 @@ def run_reference(spec, steps: int, warmup: int, budget_s: float = 90.0):
         ref = pyoracle.Reference(R=tag, flavour="fast")
     except (FileNotFoundError, OSError):
         ref = None
-    o = pyoracle.Oracle(R=R, variant="fast")
+    cores = host_cores()
+    o = pyoracle.Oracle(R=R, variant="fast", threads=cores)
     fluid, boundary = o.scene_drop(), o.scene_boundary()
-    cores = os.cpu_count() or 1
     if ref is not None:
-        cores = min(cores, ref.max_threads)
         cb = ref.init_boundary(boundary); cf = ref.ctx(len(fluid))
         du, dv = ref.compute_accel(fluid, boundary, cf, cb, *G)
         run = lambda n: ref.step(fluid, boundary, cf, cb, du, dv, n, *G, threads=cores)
@@ -239,8 +247,8 @@ def run_reference_block(spec, steps: int, warmup: int, budget_s: float, sample_p
     spacing, about `sample_particles` particles."""
     from oracle import pyoracle
     R = spec["R"]
-    o = pyoracle.Oracle(R=R, variant="fast")
-    x1, y1 = spec["block"]
+    o = pyoracle.Oracle(R=R, variant="fast", threads=host_cores())
+    x1, y1 = spec["block"] if "block" in spec else (spec["box"][1], spec["box"][3])
     ny = max(1.0, (y1 - 2 * R) / R)
     width = min(x1 - 2 * R, max(8 * 2.6 * R, sample_particles / ny * R))
     fluid = o.scene_block(2 * R, 2 * R + width, 2 * R, y1)
