@@ -39,6 +39,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "fluid-particle-updates/sec"
 UNIT = "particle-updates/s"
 G = (0.0, -9.81)
+CAP_FACTOR = 1.10        # slabs: particle slots per rank / particles uploaded to it
 
 # algorithmic HBM bytes / particle / launch (DESIGN.md "Kernels")
 ALGO_BYTES = {"advect_bin": 44.0, "reorder": 40.0, "density": 16.0, "force": 40.0}
@@ -450,7 +451,12 @@ def run_gpu_slabs(args, spec, rank, world):
     dist.broadcast_object_list(ident, src=0)
 
     def make():
-        s_ = pkg.Slab(prm, rank, world, int(cuts[rank]), int(cuts[rank + 1]), halo_capacity=halo_cap)
+        # particle slots per rank: 1.10 x its particles + four messages' worth (the library default is
+        # 1.25 x; kernels are launched for the slot capacity, so unused slots cost empty CTAs: 1.00 x
+        # measured 2 % faster than 1.25 x at N = 2).  SPHB_BENCH_CAP_FACTOR overrides (0: library default).
+        capf = float(os.environ.get("SPHB_BENCH_CAP_FACTOR", str(CAP_FACTOR)))
+        pcap = int(capf * n) + 4 * halo_cap if capf > 0 else 0
+        s_ = pkg.Slab(prm, rank, world, int(cuts[rank]), int(cuts[rank + 1]), particle_capacity=pcap, halo_capacity=halo_cap)
         return s_
     sim = make()
     sim.connect_nccl(ident[0])
@@ -575,7 +581,8 @@ def run_gpu_slabs(args, spec, rank, world):
                    "particles_per_gpu": [int(hist[int(cuts[r]):int(cuts[r + 1])].sum()) for r in range(world)],
                    "parallelism": f"x-slabs of cell columns, cuts at particle-count quantiles {[int(c) for c in cuts]}, "
                                   "2 ghost columns, one halo+migration message per neighbour per step over NCCL",
-                   "halo_message_bytes": info["message_bytes"], "deterministic_order": not args.nondeterministic,
+                   "halo_message_bytes": info["message_bytes"], "particle_slots_per_gpu": info["particle_capacity"],
+                   "deterministic_order": not args.nondeterministic,
                    "gravity": (f"tilt trace: +-{tilt[0]} deg, period {tilt[1]} steps, sample held {tilt[2]} steps, one (gx, gy) per step" if tilt else "constant (0, -9.81)"),
                    "l2": f"not flushed: per-GPU state (~100 B x {n_total / world / 1e6:.0f}M particles) is far larger than the 126 MB L2",
                    "timing": "CUDA events on the library stream around the K steps, barrier + synchronize both sides; max over ranks",
