@@ -399,7 +399,7 @@ def run_gpu(args, spec, rank, world):
            "ms_per_step_runs": [round(1e3 * r / K, 5) for r in runs],
            "path": "sphb_upload + sphb_init_boundary + sphb_compute_accel + K x sphb_step_stats(1 step) + sphb_download, pinned host buffers; median of 3 repetitions",
            "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
-    sim2.close()
+    release(sim2)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -458,8 +458,43 @@ def run_gpu_slabs(args, spec, rank, world):
         pcap = int(capf * n) + 4 * halo_cap if capf > 0 else 0
         s_ = pkg.Slab(prm, rank, world, int(cuts[rank]), int(cuts[rank + 1]), particle_capacity=pcap, halo_capacity=halo_cap)
         return s_
+    # transport of the per-step halo + migration message: "ipc" = the advect+bin kernel stores the entries
+    # straight into the neighbour's receive buffer over NVLink (CUDA IPC mapping, device-side completion
+    # signal, no NCCL call in the step); "nccl" = ncclSend/ncclRecv.  If any rank cannot map its
+    # neighbours' buffers every rank stays on NCCL, and the line says so.
+    want_ipc = os.environ.get("SPHB_BENCH_TRANSPORT", "ipc") != "nccl"
+    transport_note = []
+
+    def connect(s_, ident_):
+        s_.connect_nccl(ident_)
+        if not want_ipc:
+            return "nccl"
+        handles = [None] * world
+        dist.all_gather_object(handles, s_.ipc_handle())
+        ok, why = 1, ""
+        try:
+            s_.connect_ipc(handles)
+        except pkg.SphbError as e:
+            ok, why = 0, str(e)
+        flag = torch.tensor([ok], device=f"cuda:{dev}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            return "ipc"
+        if ok:
+            s_.disconnect_ipc()
+        if why:
+            transport_note.append(why)
+        dist.barrier()
+        return "nccl"
+
+    def release(s_):
+        if s_.info()["transport"] == 3:
+            s_.synchronize()
+            s_.disconnect_ipc()       # every rank unmaps its neighbours' blocks before anybody frees its own
+            dist.barrier()
+        s_.close()
     sim = make()
-    sim.connect_nccl(ident[0])
+    transport = connect(sim, ident[0])
     stream = torch.cuda.ExternalStream(sim.stream, device=dev)
     fl_pin = torch.empty(max(n, 1) * 7, dtype=torch.float32).pin_memory()
     fl_host = fl_pin.numpy().view(pkg.PARTICLE)[:n]
@@ -546,7 +581,7 @@ def run_gpu_slabs(args, spec, rank, world):
     sim2 = make()
     ident2 = [pkg.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ident2, src=0)
-    sim2.connect_nccl(ident2[0])
+    connect(sim2, ident2[0])
     sim2.upload(fl_host, boundary, id_base=base); sim2.init_boundary(); sim2.compute_accel(*g0); sim2.step(W, *g0); sim2.synchronize()
     trace = g_trace[:K] if tilt else np.tile(np.asarray([G], np.float32), (K, 1))
     runs, last, n_out = [], None, 0
@@ -570,7 +605,7 @@ def run_gpu_slabs(args, spec, rank, world):
            "ms_per_step_runs": [round(1e3 * r / K, 5) for r in runs],
            "path": "per rank: sphb_mg_upload + sphb_init_boundary + sphb_compute_accel + K x sphb_step_stats(1 step) + sphb_mg_download, pinned host buffers; bytes are the busiest rank's; median of 3 repetitions",
            "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
-    sim2.close()
+    release(sim2)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -580,7 +615,10 @@ def run_gpu_slabs(args, spec, rank, world):
         "config": {"workload": spec["name"], "n_fluid": n_total, "n_boundary": int(len(boundary)), "R": R,
                    "particles_per_gpu": [int(hist[int(cuts[r]):int(cuts[r + 1])].sum()) for r in range(world)],
                    "parallelism": f"x-slabs of cell columns, cuts at particle-count quantiles {[int(c) for c in cuts]}, "
-                                  "2 ghost columns, one halo+migration message per neighbour per step over NCCL",
+                                  "2 ghost columns, one halo+migration message per neighbour per step "
+                                  + ("stored by the advect+bin kernel into the neighbour's receive buffer over NVLink (CUDA IPC peer memory), completed by a device-side signal"
+                                     if transport == "ipc" else "over NCCL send/recv"),
+                   "transport": transport, **({"transport_fallback": transport_note[0][:200]} if transport_note else {}),
                    "halo_message_bytes": info["message_bytes"], "particle_slots_per_gpu": info["particle_capacity"],
                    "deterministic_order": not args.nondeterministic,
                    "gravity": (f"tilt trace: +-{tilt[0]} deg, period {tilt[1]} steps, sample held {tilt[2]} steps, one (gx, gy) per step" if tilt else "constant (0, -9.81)"),
@@ -591,7 +629,7 @@ def run_gpu_slabs(args, spec, rank, world):
                    "build": pkg.lib().sphb_build_info().decode()},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
-    sim.close()
+    release(sim)
     return line
 
 

@@ -191,9 +191,10 @@ const char *sphb_build_info(void);
  * (:93-94, cell = 2H) and keeps two ghost columns either side.  Per step each rank sends ONE
  * message to each neighbour (halo + migrants, 20 B per particle).  Call order per rank:
  *
- *   sphb_create -> sphb_mg_configure -> sphb_mg_connect_nccl | sphb_mg_connect_local
+ *   sphb_create -> sphb_mg_configure -> sphb_mg_connect_nccl [-> sphb_mg_ipc_handle, sphb_mg_connect_ipc]
+ *                                      | sphb_mg_connect_local
  *   -> sphb_mg_upload (this rank's particles, global ids) -> sphb_init_boundary
- *   -> sphb_compute_accel / sphb_step / sphb_step_trace        (NCCL transport, one process per GPU)
+ *   -> sphb_compute_accel / sphb_step / sphb_step_trace        (NCCL or peer-store transport, one process per GPU)
  *    | sphb_mg_group_compute_accel / sphb_mg_group_step       (in-process transport, one host thread)
  *   -> sphb_get_stats (this rank's owned particles) [+ sphb_mg_allreduce_stats | sphb_mg_merge_stats]
  *   -> sphb_mg_download (owned particles with their global ids)
@@ -208,7 +209,7 @@ typedef struct sphb_mg_info_t {
     int window_lo, window_hi;       /* columns held, ghosts included                */
     int halo_capacity;              /* entries per message                          */
     int particle_capacity;          /* particle slots on this rank                  */
-    int transport;                  /* 1 NCCL, 2 in-process peer stores             */
+    int transport;                  /* 1 NCCL, 2 in-process peer stores, 3 peer stores across processes (CUDA IPC) */
     unsigned long long message_bytes, bytes_sent, exchanges;
 } sphb_mg_info_t;
 
@@ -225,6 +226,18 @@ int sphb_mg_configure(sphb_ctx *ctx, int rank, int world, int col_lo, int col_hi
  * a file...), every rank connects.  libnccl.so.2 is loaded on first use. */
 int sphb_mg_unique_id(char id_out[SPHB_NCCL_ID_BYTES]);
 int sphb_mg_connect_nccl(sphb_ctx *ctx, const char id[SPHB_NCCL_ID_BYTES]);
+/* Peer-store transport across processes (one process per GPU on one NVLink/NVSwitch box): every rank
+ * exports its receive block (sphb_mg_ipc_handle), the host program hands each rank its neighbours'
+ * handles (NULL where there is no neighbour), and from then on the advect+bin kernel stores the
+ * message entries straight into the neighbour's receive buffer over NVLink; a count + epoch word
+ * written with release semantics after the kernel completes the message and the neighbour's binning
+ * kernel waits for it on the device.  No NCCL call is left in the step (an NCCL connection made
+ * before is kept for sphb_mg_allreduce_stats).  sphb_mg_disconnect_ipc unmaps the neighbours'
+ * blocks again: call it on every rank, then synchronise the ranks, before sphb_destroy. */
+#define SPHB_IPC_HANDLE_BYTES 64
+int sphb_mg_ipc_handle(sphb_ctx *ctx, unsigned char handle_out[SPHB_IPC_HANDLE_BYTES]);
+int sphb_mg_connect_ipc(sphb_ctx *ctx, const unsigned char *left_handle, const unsigned char *right_handle);
+int sphb_mg_disconnect_ipc(sphb_ctx *ctx);
 /* in-process transport: all ranks' contexts live in this process (same or different GPUs) */
 int sphb_mg_connect_local(sphb_ctx **ctxs, int n);
 

@@ -129,6 +129,9 @@ def lib() -> C.CDLL:
         "sphb_mg_unique_id": (ci, [vp]),
         "sphb_mg_connect_nccl": (ci, [vp, vp]),
         "sphb_mg_connect_local": (ci, [vp, ci]),
+        "sphb_mg_ipc_handle": (ci, [vp, vp]),
+        "sphb_mg_connect_ipc": (ci, [vp, vp, vp]),
+        "sphb_mg_disconnect_ipc": (ci, [vp]),
         "sphb_mg_upload": (ci, [vp, vp, vp, C.c_uint, ci, vp, ci]),
         "sphb_mg_download": (ci, [vp, ci, vp, vp, vp, vp, vp]),
         "sphb_mg_upload_accel": (ci, [vp, vp, vp]),
@@ -371,6 +374,7 @@ class MgInfo(C.Structure):
 
 
 NCCL_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 def grid_columns(prm: Params):
@@ -436,6 +440,22 @@ class Slab(Simulation):
 
     def connect_nccl(self, unique_id: bytes):
         _check(lib().sphb_mg_connect_nccl(self._h, C.c_char_p(unique_id)), "sphb_mg_connect_nccl")
+
+    # peer-store transport across processes (sphb_mg_connect_ipc): every rank exports its receive block,
+    # the ranks exchange the handles (any channel) and map their neighbours' blocks
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib().sphb_mg_ipc_handle(self._h, buf), "sphb_mg_ipc_handle")
+        return buf.raw
+
+    def connect_ipc(self, handles):
+        """handles: every rank's ipc_handle(), indexed by rank."""
+        left = handles[self.rank - 1] if self.rank > 0 else None
+        right = handles[self.rank + 1] if self.rank < self.world - 1 else None
+        _check(lib().sphb_mg_connect_ipc(self._h, left, right), "sphb_mg_connect_ipc")
+
+    def disconnect_ipc(self):
+        _check(lib().sphb_mg_disconnect_ipc(self._h), "sphb_mg_disconnect_ipc")
 
     def upload(self, fluid: np.ndarray, boundary: np.ndarray | None = None, ids: np.ndarray | None = None,
                id_base: int = 0):

@@ -109,6 +109,53 @@ int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool ad
     return 1;
 }
 
+// ---- peer-store transport across processes: message completion on the device -------------------
+// The advect+bin kernel has stored this rank's message entries into the neighbours' receive buffers
+// (peer memory over NVLink).  This one-warp kernel follows it on the stream: lane `side` publishes
+// (epoch << 32 | count) into the neighbour's message header with a system-scope release store, so the
+// entries are visible there before the word is.  The neighbour's k_bin_recv waits for the epoch.
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(32)
+k_halo_signal(const SlabIO io, const uint32_t epoch)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int side = threadIdx.x;
+    if (side < 2 && io.has[side]) {
+        const uint32_t cnt = *io.send_cnt[side];
+        __threadfence_system();
+        st_release_sys_u64(reinterpret_cast<unsigned long long *>(io.send[side].hdr()),
+                           ((unsigned long long)epoch << 32) | cnt);
+    }
+}
+
+int launch_halo_signal(cudaStream_t st, const SlabIO &io, uint32_t epoch)
+{
+    launch_pdl(st, 1, 32, k_halo_signal, io, epoch);
+    return 1;
+}
+
+// how long k_bin_recv waits for a neighbour's message before it gives up (a dead neighbour must not
+// hang this GPU): the slab is then flagged (overflow word, bit 30) and the step goes on without it
+constexpr unsigned long long kHaloWaitNs = 20ULL * 1000ULL * 1000ULL * 1000ULL;
+constexpr unsigned int kHaloTimeoutFlag = 1u << 30;
+
 // Received halo / migrant entries become slots n_cur .. n_cur + count_left + count_right - 1 of the
 // build input and are binned like the rest.
 __global__ void __launch_bounds__(kStreamThreads)
@@ -117,11 +164,36 @@ k_bin_recv(const Consts k, const SlabIO io, const int *__restrict__ n_cur, int *
            uint32_t *__restrict__ key, uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count,
            DeviceCounters *__restrict__ ctr)
 {
+    __shared__ uint32_t s_cnt[2];
     pdl_trigger();
     pdl_wait();
     const uint32_t cap = (uint32_t)io.recv[0].cap;
-    uint32_t cl = io.has[0] ? io.recv[0].hdr()[0] : 0u;
-    uint32_t cr = io.has[1] ? io.recv[1].hdr()[0] : 0u;
+    if (io.wait_epoch) {
+        // peer-store transport: the neighbour's signal kernel publishes (count, epoch) when its message
+        // is complete; one thread per side polls this rank's own memory
+        if (threadIdx.x < 2) {
+            const int side = threadIdx.x;
+            uint32_t c = 0u;
+            if (io.has[side]) {
+                const uint32_t *h = io.recv[side].hdr();
+                const unsigned long long t0 = global_timer_ns();
+                bool ok;
+                while (!(ok = ld_acquire_sys_u32(h + 1) == io.wait_epoch)) {
+                    if (global_timer_ns() - t0 > kHaloWaitNs) break;
+                    __nanosleep(100);
+                }
+                if (ok) c = ld_acquire_sys_u32(h);
+                else if (blockIdx.x == 0) atomicOr(io.overflow, kHaloTimeoutFlag);
+            }
+            s_cnt[side] = c;
+        }
+        __syncthreads();
+    } else {
+        if (threadIdx.x < 2) s_cnt[threadIdx.x] = io.has[threadIdx.x] ? io.recv[threadIdx.x].hdr()[0] : 0u;
+        __syncthreads();
+    }
+    uint32_t cl = s_cnt[0];
+    uint32_t cr = s_cnt[1];
     cl = cl < cap ? cl : cap;
     cr = cr < cap ? cr : cap;
     const int n0 = *n_cur;
@@ -138,10 +210,11 @@ k_bin_recv(const Consts k, const SlabIO io, const int *__restrict__ n_cur, int *
     const uint32_t e = t < cl ? t : t - cl;
     const long long slot = (long long)n0 + t;
     if (slot >= io.capacity) { atomicAdd(io.overflow, 1u); return; }
-    const float2 p = b.pos()[e];
+    // through L2 (the peer-store transport's entries arrive there from another GPU)
+    const float2 p = __ldcg(b.pos() + e);
     pos[slot] = p;
-    vel[slot] = b.vel()[e];
-    id[slot] = b.id()[e];
+    vel[slot] = __ldcg(b.vel() + e);
+    id[slot] = __ldcg(b.id() + e);
     int row, col;
     bool clamped, outside;
     cell_of_window(k, p.x, p.y, row, col, clamped, outside);

@@ -400,9 +400,9 @@ int sphb_compute_accel(sphb_ctx *c, float gx, float gy)
     if (c->fluid.n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
     if (c->boundary.n > 0 && !c->boundary_ready) { set_error("sphb_init_boundary not called"); return SPHB_E_STATE; }
     if (c->mg.on) {
-        if (c->mg.transport != 1) { set_error("slab not connected over NCCL: use sphb_mg_group_compute_accel"); return SPHB_E_STATE; }
+        if (c->mg.transport != 1 && c->mg.transport != 3) { set_error("slab not connected over NCCL or peer stores: use sphb_mg_group_compute_accel"); return SPHB_E_STATE; }
         step_phase_a(c, false);
-        int rc = mg_exchange_nccl(c);
+        int rc = mg_exchange(c);
         if (rc) return rc;
         step_phase_b(c, gx, gy, false);
     } else {
@@ -447,7 +447,7 @@ static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int ns
     if (nsteps < 0) return SPHB_E_ARG;
     if (c->fluid.n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
     if (!c->accel_ready) { set_error("sphb_compute_accel must run before sphb_step (:604-607 precede :610)"); return SPHB_E_STATE; }
-    if (c->mg.on && c->mg.transport != 1) { set_error("slab not connected over NCCL: use sphb_mg_group_step"); return SPHB_E_STATE; }
+    if (c->mg.on && c->mg.transport != 1 && c->mg.transport != 3) { set_error("slab not connected over NCCL or peer stores: use sphb_mg_group_step"); return SPHB_E_STATE; }
     StepStats ss;
     if (stats_out && nsteps > 0) {
         ss.block = reinterpret_cast<unsigned long long *>(c->d_stats);
@@ -463,7 +463,7 @@ static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int ns
         const bool with_stats = stats_out && s == nsteps - 1;
         if (c->mg.on) {
             step_phase_a(c, true);
-            int rc = mg_exchange_nccl(c);
+            int rc = mg_exchange(c);
             if (rc) return rc;
             step_phase_b(c, gx, gy, true, with_stats ? &ss : nullptr);
         } else {

@@ -103,6 +103,9 @@ struct SlabIO {
     unsigned int *lost = nullptr;                 // particles that left the window without a taker
     unsigned int *overflow = nullptr;             // message or slot capacity exceeded
     int capacity = 0;                             // allocated particle slots
+    // peer stores across processes: the binning kernel waits until hdr()[1] of each receive buffer
+    // carries this epoch (0: the message is complete by stream order, nothing to wait for)
+    uint32_t wait_epoch = 0;
 };
 
 // A sorted particle set: SoA in HBM, permanently ordered by cell (row-major, the
@@ -182,13 +185,17 @@ struct MgState {
     bool on = false;
     int rank = 0, world = 1;
     int col_lo = 0, col_hi = 0;          // owned global columns [col_lo, col_hi)
-    int transport = 0;                   // 0: not connected, 1: NCCL (one process per GPU), 2: in-process peers
+    int transport = 0;                   // 0: not connected, 1: NCCL (one process per GPU), 2: in-process peers,
+                                         // 3: peer stores across processes (CUDA IPC)
     void *nccl_comm = nullptr;           // ncclComm_t
     int halo_cap = 0;                    // entries per message
     int capacity = 0;                    // particle slots
     Consts k_global;                     // the unwindowed grid (boundary pseudo-mass pass)
     unsigned char *d_send[2] = {nullptr, nullptr};
-    unsigned char *d_recv[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][step parity]
+    unsigned char *d_recv[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][step parity], inside d_recv_block
+    unsigned char *d_recv_block = nullptr;   // one allocation (one IPC handle): 4 messages, recv_stride apart
+    size_t recv_stride = 0;
+    unsigned char *ipc_peer_block[2] = {nullptr, nullptr};    // the neighbours' receive blocks mapped here
     uint32_t *d_send_cnt = nullptr;      // 2 words (in-process transport; NCCL counts in the message header)
     unsigned int *d_flags = nullptr;     // [0] lost, [1] overflow
     int *d_counts = nullptr;             // [0] n_cur, [1] n_in (fluid), [2] boundary n
@@ -293,6 +300,8 @@ int free_set_public(ParticleSet &ps);
 // sphb_mg.cu
 SlabIO mg_slab_io(const sphb_ctx *c);
 int mg_exchange_nccl(sphb_ctx *c);
+int mg_exchange(sphb_ctx *c);            // the transport's part of a step between phase A and phase B
+int launch_halo_signal(cudaStream_t st, const SlabIO &io, uint32_t epoch);
 int mg_init_boundary(sphb_ctx *c);
 void mg_free(sphb_ctx *c);
 

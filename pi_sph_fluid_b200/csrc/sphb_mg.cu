@@ -20,6 +20,10 @@
 //   in-process  one host thread drives several contexts (sphb_mg_group_*): the advect+bin kernel
 //               stores message entries straight into the neighbour's receive buffer (peer memory
 //               over NVLink when the slabs sit on different GPUs), ordered by CUDA events.
+//   peer/IPC    one process per GPU, the same peer stores: every rank maps its neighbours' receive
+//               blocks (cudaIpc*), a one-warp kernel publishes (count, epoch) with a system-scope
+//               release store once the advect+bin kernel is complete, and the neighbour's binning
+//               kernel waits for that word on the device.  No NCCL call in the step.
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -101,6 +105,11 @@ SlabIO mg_slab_io(const sphb_ctx *c)
             io.send[side].base = m.peer[side] ? m.peer[side]->mg.d_recv[1 - side][q] : nullptr;
             io.send_cnt[side] = m.d_send_cnt + side;
             io.recv[side].base = m.d_recv[side][q];
+        } else if (m.transport == 3) {
+            // the same across processes: the neighbour's block is mapped here, laid out like ours
+            io.send[side].base = m.ipc_peer_block[side] + (size_t)((1 - side) * 2 + q) * m.recv_stride;
+            io.send_cnt[side] = m.d_send_cnt + side;
+            io.recv[side].base = m.d_recv[side][q];
         } else {
             io.send[side].base = m.d_send[side];
             io.send_cnt[side] = reinterpret_cast<uint32_t *>(m.d_send[side]);
@@ -113,6 +122,8 @@ SlabIO mg_slab_io(const sphb_ctx *c)
     io.lost = m.d_flags;
     io.overflow = m.d_flags + 1;
     io.capacity = m.capacity;
+    // every rank makes the same number of exchanges, so the count doubles as the message's epoch
+    io.wait_epoch = m.transport == 3 ? (uint32_t)(m.exchanges + 1ULL) : 0u;
     return io;
 }
 
@@ -137,6 +148,24 @@ int mg_exchange_nccl(sphb_ctx *c)
     }
     SPHB_NCCL(g_nccl.GroupEnd());
     return SPHB_OK;
+}
+
+// peer stores across processes: the entries are already in the neighbours' buffers; publish the
+// counts behind them (k_halo_signal).  The waiting side is k_bin_recv (SlabIO::wait_epoch).
+static int mg_exchange_ipc(sphb_ctx *c)
+{
+    MgState &m = c->mg;
+    if (m.world == 1) return SPHB_OK;
+    const SlabIO io = mg_slab_io(c);
+    c->launches += launch_halo_signal(c->stream, io, io.wait_epoch);
+    for (int side = 0; side < 2; side++)
+        if (io.has[side]) m.halo_bytes += 8;      // the entries themselves are counted on the device only
+    return SPHB_OK;
+}
+
+int mg_exchange(sphb_ctx *c)
+{
+    return c->mg.transport == 3 ? mg_exchange_ipc(c) : mg_exchange_nccl(c);
 }
 
 // :600-601 on a slab.  psi needs every boundary neighbour, so it is computed once on the whole
@@ -177,10 +206,10 @@ void mg_free(sphb_ctx *c)
     if (!m.on) return;
     if (m.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(m.nccl_comm));
     for (int s = 0; s < 2; s++) {
+        if (m.ipc_peer_block[s]) cudaIpcCloseMemHandle(m.ipc_peer_block[s]);
         cudaFree(m.d_send[s]);
-        cudaFree(m.d_recv[s][0]);
-        cudaFree(m.d_recv[s][1]);
     }
+    cudaFree(m.d_recv_block);
     cudaFree(m.d_send_cnt); cudaFree(m.d_flags); cudaFree(m.d_counts);
     if (m.ev_sent) cudaEventDestroy(m.ev_sent);
     m = MgState();
@@ -228,11 +257,14 @@ int sphb_mg_configure(sphb_ctx *c, int rank, int world, int col_lo, int col_hi, 
     SPHB_CUDA(cudaMemset(c->scan.tile_state, 0, sizeof(unsigned long long) * (c->scan.n_tiles + 1)));
 
     const size_t bytes = msg_bytes(m.halo_cap);
+    // the four receive buffers [side][parity] share one allocation, so one IPC handle exports them
+    m.recv_stride = (bytes + 255) & ~(size_t)255;
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_recv_block), 4 * m.recv_stride));
     for (int s = 0; s < 2; s++) {
         SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_send[s]), bytes));
         SPHB_CUDA(cudaMemset(m.d_send[s], 0, 16));
         for (int q = 0; q < 2; q++) {
-            SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_recv[s][q]), bytes));
+            m.d_recv[s][q] = m.d_recv_block + (size_t)(s * 2 + q) * m.recv_stride;
             SPHB_CUDA(cudaMemset(m.d_recv[s][q], 0, 16));
         }
     }
@@ -275,6 +307,64 @@ int sphb_mg_connect_nccl(sphb_ctx *c, const char *id_in)
     SPHB_NCCL(g_nccl.CommInitRank(&comm, c->mg.world, id, c->mg.rank));
     c->mg.nccl_comm = comm;
     c->mg.transport = 1;
+    return SPHB_OK;
+}
+
+int sphb_mg_ipc_handle(sphb_ctx *c, unsigned char *handle_out)
+{
+    SPHB_ENTER(c);
+    if (!c->mg.on) { set_error("sphb_mg_configure first"); return SPHB_E_STATE; }
+    if (!handle_out) return SPHB_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= SPHB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t grew");
+    cudaIpcMemHandle_t h;
+    SPHB_CUDA(cudaIpcGetMemHandle(&h, c->mg.d_recv_block));
+    memset(handle_out, 0, SPHB_IPC_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof h);
+    return SPHB_OK;
+}
+
+int sphb_mg_connect_ipc(sphb_ctx *c, const unsigned char *left_handle, const unsigned char *right_handle)
+{
+    SPHB_ENTER(c);
+    MgState &m = c->mg;
+    if (!m.on) { set_error("sphb_mg_configure first"); return SPHB_E_STATE; }
+    if (m.transport == 2 || m.transport == 3) { set_error("already connected (transport %d)", m.transport); return SPHB_E_STATE; }
+    if (m.exchanges != 0) { set_error("connect before the first step: the exchange count is the message epoch"); return SPHB_E_STATE; }
+    const unsigned char *hs[2] = {left_handle, right_handle};
+    const bool need[2] = {m.rank > 0, m.rank < m.world - 1};
+    for (int side = 0; side < 2; side++)
+        if (need[side] != (hs[side] != nullptr)) {
+            set_error("rank %d of %d: %s handle %s", m.rank, m.world, side ? "right" : "left", need[side] ? "missing" : "given without a neighbour");
+            return SPHB_E_ARG;
+        }
+    for (int side = 0; side < 2; side++) {
+        if (!need[side]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs[side], sizeof h);
+        void *p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int s2 = 0; s2 < side; s2++)
+                if (m.ipc_peer_block[s2]) { cudaIpcCloseMemHandle(m.ipc_peer_block[s2]); m.ipc_peer_block[s2] = nullptr; }
+            set_error("cudaIpcOpenMemHandle (%s neighbour): %s", side ? "right" : "left", cudaGetErrorString(e));
+            return SPHB_E_COMM;
+        }
+        m.ipc_peer_block[side] = static_cast<unsigned char *>(p);
+    }
+    m.transport = 3;
+    return SPHB_OK;
+}
+
+int sphb_mg_disconnect_ipc(sphb_ctx *c)
+{
+    SPHB_ENTER(c);
+    MgState &m = c->mg;
+    if (m.transport != 3) return SPHB_OK;
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int side = 0; side < 2; side++)
+        if (m.ipc_peer_block[side]) { SPHB_CUDA(cudaIpcCloseMemHandle(m.ipc_peer_block[side])); m.ipc_peer_block[side] = nullptr; }
+    m.transport = m.nccl_comm ? 1 : 0;
     return SPHB_OK;
 }
 
@@ -549,7 +639,7 @@ int sphb_mg_allreduce_stats(sphb_ctx *c, sphb_stats *inout)
     SPHB_ENTER(c);
     if (!inout) return SPHB_E_ARG;
     MgState &m = c->mg;
-    if (!m.on || m.transport != 1) { set_error("not an NCCL slab context"); return SPHB_E_STATE; }
+    if (!m.on || (!m.nccl_comm && m.world > 1)) { set_error("not an NCCL slab context (sphb_mg_connect_nccl)"); return SPHB_E_STATE; }
     if (m.world == 1) return SPHB_OK;
     int rc = ensure_stage(c, 256);
     if (rc) return rc;

@@ -1,10 +1,12 @@
-"""NCCL transport of the slab path, one process per GPU.  Run as
+"""The one-process-per-GPU transports of the slab path.  Run as
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/mg_nccl_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/mg_nccl_check.py [nccl|ipc]
 
 Every rank builds its slab of the scene, the ranks step together through sphb_step (halo +
-migration over ncclSend/ncclRecv), rank 0 gathers the owned particles and compares them BIT FOR
-BIT with a single-GPU run of the same scene.  Prints "mg_nccl_check ok"."""
+migration over ncclSend/ncclRecv, or — "ipc" — stored by the advect+bin kernel straight into the
+neighbour's receive buffer over NVLink and completed by a device-side signal), rank 0 gathers the
+owned particles and compares them BIT FOR BIT with a single-GPU run of the same scene.
+Prints "mg_nccl_check ok" / "mg_ipc_check ok"."""
 import os
 import sys
 from pathlib import Path
@@ -19,6 +21,7 @@ import pi_sph_fluid_b200 as pkg  # noqa: E402
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    transport = sys.argv[1] if len(sys.argv) > 1 else "nccl"
     dev = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
@@ -33,6 +36,11 @@ def main():
     dist.broadcast_object_list(ident, src=0)
     slab = pkg.Slab(prm, rank, world, int(cuts[rank]), int(cuts[rank + 1]), halo_capacity=16384)
     slab.connect_nccl(ident[0])
+    if transport == "ipc":
+        handles = [None] * world
+        dist.all_gather_object(handles, slab.ipc_handle())
+        slab.connect_ipc(handles)
+        assert slab.info()["transport"] == 3
     slab.upload(part, boundary, id_base=base)
     slab.init_boundary()
     slab.compute_accel(*g)
@@ -61,16 +69,19 @@ def main():
         ok &= abs(st["kinetic"] - rst["kinetic"]) <= 1e-9 * abs(rst["kinetic"]) and st["max_speed"] == rst["max_speed"]
         moved = sum(int(((pkg.columns_of(prm, ff["x"]) < cuts[r]) | (pkg.columns_of(prm, ff["x"]) >= cuts[r + 1])).sum())
                     for r, (i, ff, a, b) in enumerate(gathered))
-        print(f"world {world}: {len(full)} particles, {steps} steps, owned-out-of-slab {moved}, "
+        print(f"world {world} ({transport}): {len(full)} particles, {steps} steps, owned-out-of-slab {moved}, "
               f"message {info['message_bytes']} B, sent {info['bytes_sent']} B, identical={ok}")
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{dev}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if transport == "ipc":
+        slab.disconnect_ipc()          # unmap the neighbours' blocks on every rank before anybody frees its own
+        dist.barrier()
     slab.close()
     dist.destroy_process_group()
     if int(flag.item()) != 1:
         sys.exit(1)
     if rank == 0:
-        print("mg_nccl_check ok")
+        print(f"mg_{transport}_check ok")
 
 
 if __name__ == "__main__":

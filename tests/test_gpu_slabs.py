@@ -186,14 +186,45 @@ def test_slab_api_misuse(lib_built):
     s.close()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_nccl_transport_under_torchrun(lib_built, world):
+@pytest.mark.parametrize("world,transport", [(2, "nccl"), (2, "ipc")])
+def test_process_per_gpu_transports_under_torchrun(lib_built, world, transport):
+    """One process per GPU: halo + migration over ncclSend/ncclRecv, and as peer stores into the
+    neighbour's receive buffer (CUDA IPC) completed by a device-side signal — both bit-identical to
+    the single-GPU run."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(ROOT / "tests" / "mg_nccl_check.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", "29631" if transport == "nccl" else "29633",
+                        str(ROOT / "tests" / "mg_nccl_check.py"), transport],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "mg_nccl_check ok" in r.stdout
+    assert f"mg_{transport}_check ok" in r.stdout
+
+
+def test_ipc_transport_single_process_loopback(lib_built):
+    """World 1 has no neighbour: connecting the peer-store transport needs no handle and the slab
+    steps like a single-GPU run; a handle without a neighbour is refused."""
+    pkg = lib_built
+    prm = pkg.default_params(0.02)
+    fluid, boundary = pkg.scene_drop(prm), pkg.scene_boundary(prm)
+    _, cols = pkg.grid_columns(prm)
+    rf, rdu, rdv, _ = single_gpu(pkg, prm, fluid, boundary, 50, (0.0, -9.81))
+    s = pkg.Slab(prm, 0, 1, 0, cols)
+    h = s.ipc_handle()
+    assert len(h) == pkg.api.IPC_HANDLE_BYTES and any(h)
+    with pytest.raises(pkg.SphbError):
+        pkg.api._check(pkg.lib().sphb_mg_connect_ipc(s._h, h, None), "sphb_mg_connect_ipc")
+    s.connect_ipc([h])
+    assert s.info()["transport"] == 3
+    s.upload(fluid, boundary, ids=np.arange(len(fluid), dtype=np.uint32))
+    s.init_boundary()
+    s.compute_accel(0.0, -9.81)
+    s.step(50, 0.0, -9.81)
+    ids, f, du, dv = s.download()
+    s.disconnect_ipc()
+    s.close()
+    out = np.zeros(len(fluid), pkg.PARTICLE); odu = np.zeros(len(fluid), np.float32); odv = np.zeros(len(fluid), np.float32)
+    out[ids] = f; odu[ids] = du; odv[ids] = dv
+    assert_identical(out, odu, odv, rf, rdu, rdv)
