@@ -25,7 +25,7 @@ def main():
     dev = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
-    R, steps, g = 0.01, 300, (3.0, -9.81)
+    R, steps, g = 0.01, 400, (60.0, -9.81)     # strong sideways pull: particles cross the cuts
     prm = pkg.default_params(R, device=dev)
     box = (2 * R, 1.5, 2 * R, 0.6)
     cuts = pkg.plan_cuts(pkg.scene_block_column_hist(prm, *box), world)
