@@ -23,6 +23,7 @@ Keys of the JSON line (see the round prompt for the contract):
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -379,10 +380,13 @@ def run_gpu(args, spec, rank, world):
         sim2.upload(fl_host, bd_host)                      # H2D: 28 B x (n_fluid + n_boundary)
         sim2.init_boundary()
         sim2.compute_accel(*G)
+        st = pkg.Stats()
+        st_ref, g_addr = ctypes.byref(st), trace.ctypes.data
         for s in range(K):
             # that step's gravity sample in (8 B); the step's statistics (:656-675) out: 136 B written by
-            # the force pass into mapped pinned host memory
-            last = sim2.step_stats(trace[s:s + 1])
+            # the force pass into mapped pinned host memory (one sphb_step_stats call per step)
+            sim2.step_stats_into(g_addr + 8 * s, 1, st_ref)
+        last = st.asdict()
         sim2.download_into(out_host, du_pin.numpy(), dv_pin.numpy())     # D2H: 36 B x n_fluid
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
@@ -399,7 +403,7 @@ def run_gpu(args, spec, rank, world):
            "ms_per_step_runs": [round(1e3 * r / K, 5) for r in runs],
            "path": "sphb_upload + sphb_init_boundary + sphb_compute_accel + K x sphb_step_stats(1 step) + sphb_download, pinned host buffers; median of 3 repetitions",
            "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
-    release(sim2)
+    sim2.close()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -565,12 +569,18 @@ def run_gpu_slabs(args, spec, rank, world):
             kern[name] = {"ms": round(ms, 5)}
             if name in ALGO_BYTES:
                 kern[name]["algo_GBps"] = round(ALGO_BYTES[name] * n_local / (ms * 1e-3) / 1e9, 2)
+    # every rank's per-kernel times (ms per launch, rank order): "other" is the binning of the received
+    # entries, which on the peer-store transport includes the wait for the neighbours' signals
+    all_kern = [None] * world
+    dist.all_gather_object(all_kern, {name: d["ms"] for name, d in kern.items()})
+    per_rank_ms = {name: [round(k_.get(name, 0.0), 4) for k_ in all_kern] for name in kern}
     force_ms = prof["force"]["ms"] / max(1, prof["force"]["launches"])
     dens_ms = prof["density"]["ms"] / max(1, prof["density"]["launches"])
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     # per-GPU load is the 8M-particle dam-break slab: the committed ncu capture of dam8m is the matching one
     roofline = make_roofline("dam8m", n_local, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_max_mhz, peak_src,
                              sm_count, suffix=" (rank 0)")
+    roofline["kernels_per_rank_ms"] = per_rank_ms
 
     # ---- e2e: host buffers -> C ABI -> host buffers on every rank
     pcap = info["particle_capacity"]
@@ -583,7 +593,7 @@ def run_gpu_slabs(args, spec, rank, world):
     dist.broadcast_object_list(ident2, src=0)
     connect(sim2, ident2[0])
     sim2.upload(fl_host, boundary, id_base=base); sim2.init_boundary(); sim2.compute_accel(*g0); sim2.step(W, *g0); sim2.synchronize()
-    trace = g_trace[:K] if tilt else np.tile(np.asarray([G], np.float32), (K, 1))
+    trace = np.ascontiguousarray(g_trace[:K] if tilt else np.tile(np.asarray([G], np.float32), (K, 1)), np.float32)
     runs, last, n_out = [], None, 0
     for _rep in range(3):
         barrier()
@@ -591,8 +601,11 @@ def run_gpu_slabs(args, spec, rank, world):
         sim2.upload(fl_host, boundary, id_base=base)
         sim2.init_boundary()
         sim2.compute_accel(*g0)
+        st_ = pkg.Stats()
+        st_ref, g_addr = ctypes.byref(st_), trace.ctypes.data
         for s_ in range(K):
-            last = sim2.step_stats(trace[s_:s_ + 1])
+            sim2.step_stats_into(g_addr + 8 * s_, 1, st_ref)
+        last = st_.asdict()
         n_out = sim2.download_into(out_host, ids_host, du_host, dv_host)
         torch.cuda.synchronize()
         runs.append(max_over_ranks(time.perf_counter() - t0))

@@ -276,6 +276,13 @@ class Simulation:
         _check(lib().sphb_step_stats(self._h, _p(g), len(g), C.byref(st)), "sphb_step_stats")
         return st.asdict()
 
+    def step_stats_into(self, g_addr: int, nsteps: int, st_ref) -> None:
+        """step_stats without per-call allocations, for host loops that call it once per step:
+        g_addr = address of nsteps float32 (gx, gy) pairs, st_ref = ctypes.byref(Stats()) made once."""
+        rc = lib().sphb_step_stats(self._h, g_addr, nsteps, st_ref)
+        if rc < 0:
+            _check(rc, "sphb_step_stats")
+
     def synchronize(self):
         _check(lib().sphb_synchronize(self._h), "sphb_synchronize")
 

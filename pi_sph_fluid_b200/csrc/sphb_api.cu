@@ -346,20 +346,21 @@ int sphb_upload(sphb_ctx *c, const sphb_particle *fluid, int n_fluid, const sphb
         set_error("bad particle arrays"); return SPHB_E_ARG;
     }
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t fb = (size_t)n_fluid * sizeof(sphb_particle), bb = (size_t)n_boundary * sizeof(sphb_particle);
+    int rc = ensure_stage(c, (fb > bb ? fb : bb) + 16);
+    if (rc) return rc;
+    // the copy is on its way while the host looks at the masses
+    if (n_fluid > 0) SPHB_CUDA(cudaMemcpyAsync(c->d_stage, fluid, fb, cudaMemcpyHostToDevice, c->stream));
     // uniform fluid mass (the reference sets every m = RHO_0*V, :502) selects the kernels
     // that keep the mass in the constant bank
     bool uniform = true;
     for (int i = 1; i < n_fluid && uniform; i++) uniform = (memcmp(&fluid[i].m, &fluid[0].m, sizeof(float)) == 0);
-    int rc = alloc_set(c->fluid, n_fluid, c->k.ncells, false, !uniform);
+    rc = alloc_set(c->fluid, n_fluid, c->k.ncells, false, !uniform);
     if (rc) return rc;
     c->fluid.uniform_mass = uniform;
     c->fluid.uniform_mass_value = n_fluid > 0 ? fluid[0].m : c->prm.rho0 * c->prm.vol;
     c->k.mass = c->fluid.uniform_mass_value;
-    const size_t fb = (size_t)n_fluid * sizeof(sphb_particle), bb = (size_t)n_boundary * sizeof(sphb_particle);
-    rc = ensure_stage(c, (fb > bb ? fb : bb) + 16);
-    if (rc) return rc;
     if (n_fluid > 0) {
-        SPHB_CUDA(cudaMemcpyAsync(c->d_stage, fluid, fb, cudaMemcpyHostToDevice, c->stream));
         c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(c->d_stage), c->fluid, false);
         SPHB_CUDA(cudaStreamSynchronize(c->stream));     // d_stage is reused below
     }

@@ -408,11 +408,6 @@ int sphb_mg_upload(sphb_ctx *c, const sphb_particle *fluid, const uint32_t *ids,
     if (n_fluid < 0 || n_boundary < 0 || (n_fluid > 0 && !fluid) || (n_boundary > 0 && !boundary)) {
         set_error("bad particle arrays"); return SPHB_E_ARG;
     }
-    for (int i = 1; i < n_fluid; i++)
-        if (memcmp(&fluid[i].m, &fluid[0].m, sizeof(float)) != 0) {
-            set_error("slab contexts need a uniform fluid mass (the reference's m = RHO_0*V, :502)");
-            return SPHB_E_ARG;
-        }
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
     if (m.capacity <= 0) m.capacity = n_fluid + n_fluid / 4 + 4 * m.halo_cap + 1024;
     if (m.capacity < n_fluid + 2 * m.halo_cap) { set_error("particle capacity %d too small for %d particles + two messages", m.capacity, n_fluid); return SPHB_E_ARG; }
@@ -437,6 +432,14 @@ int sphb_mg_upload(sphb_ctx *c, const sphb_particle *fluid, const uint32_t *ids,
         uint32_t *d_ids = ids ? reinterpret_cast<uint32_t *>(base + ((fb + 15) & ~(size_t)15)) : nullptr;
         SPHB_CUDA(cudaMemcpyAsync(base, fluid, fb, cudaMemcpyHostToDevice, c->stream));
         if (ids) SPHB_CUDA(cudaMemcpyAsync(d_ids, ids, ib, cudaMemcpyHostToDevice, c->stream));
+        // while the copies are on their way the host checks the masses
+        for (int i = 1; i < n_fluid; i++)
+            if (memcmp(&fluid[i].m, &fluid[0].m, sizeof(float)) != 0) {
+                cudaStreamSynchronize(c->stream);
+                f.n = 0;
+                set_error("slab contexts need a uniform fluid mass (the reference's m = RHO_0*V, :502)");
+                return SPHB_E_ARG;
+            }
         c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(base), f, false, n_fluid, d_ids, id_base);
     } else {
         f.pc = f.vc = f.ic = f.mc = f.xc = 0;

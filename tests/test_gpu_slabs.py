@@ -179,6 +179,10 @@ def test_slab_api_misuse(lib_built):
     with pytest.raises(pkg.SphbError):
         pkg.Simulation.upload(s, pkg.scene_drop(prm))     # plain upload on a slab context
     fluid = pkg.scene_drop(prm)
+    uneven = fluid[:10].copy()
+    uneven["m"][3] *= 1.5
+    with pytest.raises(pkg.SphbError):
+        s.upload(uneven, pkg.scene_boundary(prm), ids=np.arange(10))     # slabs need the reference's uniform mass (:502)
     s.upload(fluid[:10], pkg.scene_boundary(prm), ids=np.arange(10))
     s.init_boundary()
     with pytest.raises(pkg.SphbError):
