@@ -382,10 +382,17 @@ def run_gpu(args, spec, rank, world):
         sim2.compute_accel(*G)
         st = pkg.Stats()
         st_ref, g_addr = ctypes.byref(st), trace.ctypes.data
+        prev = None
         for s in range(K):
             # that step's gravity sample in (8 B); the step's statistics (:656-675) out: 136 B written by
-            # the force pass into mapped pinned host memory (one sphb_step_stats call per step)
-            sim2.step_stats_into(g_addr + 8 * s, 1, st_ref)
+            # the force pass into mapped pinned host memory.  The host launches step s, then reads the
+            # statistics of step s - 1 (sphb_step_stats_begin / _end): every step's result is read, and the
+            # GPU does not idle while the host picks it up.
+            t = sim2.step_stats_begin(g_addr + 8 * s, 1)
+            if prev is not None:
+                sim2.step_stats_end(prev, st_ref)
+            prev = t
+        sim2.step_stats_end(prev, st_ref)
         last = st.asdict()
         sim2.download_into(out_host, du_pin.numpy(), dv_pin.numpy())     # D2H: 36 B x n_fluid
         torch.cuda.synchronize()
@@ -401,7 +408,7 @@ def run_gpu(args, spec, rank, world):
     e2e = {"value": total_particles * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": round(h2d, 1),
            "d2h_bytes_per_step": round(d2h, 1), "ms_per_step": round(1e3 * e2e_s / K, 5),
            "ms_per_step_runs": [round(1e3 * r / K, 5) for r in runs],
-           "path": "sphb_upload + sphb_init_boundary + sphb_compute_accel + K x sphb_step_stats(1 step) + sphb_download, pinned host buffers; median of 3 repetitions",
+           "path": "sphb_upload + sphb_init_boundary + sphb_compute_accel + K x (sphb_step_stats_begin(1 step), sphb_step_stats_end(previous step)) + sphb_download, pinned host buffers; every step's statistics are read on the host, one step behind the launches; median of 3 repetitions",
            "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
     sim2.close()
 
@@ -603,8 +610,13 @@ def run_gpu_slabs(args, spec, rank, world):
         sim2.compute_accel(*g0)
         st_ = pkg.Stats()
         st_ref, g_addr = ctypes.byref(st_), trace.ctypes.data
+        prev = None
         for s_ in range(K):
-            sim2.step_stats_into(g_addr + 8 * s_, 1, st_ref)
+            t = sim2.step_stats_begin(g_addr + 8 * s_, 1)      # launch step s_, then read step s_ - 1's statistics
+            if prev is not None:
+                sim2.step_stats_end(prev, st_ref)
+            prev = t
+        sim2.step_stats_end(prev, st_ref)
         last = st_.asdict()
         n_out = sim2.download_into(out_host, ids_host, du_host, dv_host)
         torch.cuda.synchronize()
@@ -616,7 +628,7 @@ def run_gpu_slabs(args, spec, rank, world):
            "h2d_bytes_per_step": round(28 * (n_max + len(boundary)) / K + 8, 1),
            "d2h_bytes_per_step": round(40 * n_max / K + 136, 1), "ms_per_step": round(1e3 * e2e_s / K, 5),
            "ms_per_step_runs": [round(1e3 * r / K, 5) for r in runs],
-           "path": "per rank: sphb_mg_upload + sphb_init_boundary + sphb_compute_accel + K x sphb_step_stats(1 step) + sphb_mg_download, pinned host buffers; bytes are the busiest rank's; median of 3 repetitions",
+           "path": "per rank: sphb_mg_upload + sphb_init_boundary + sphb_compute_accel + K x (sphb_step_stats_begin(1 step), sphb_step_stats_end(previous step)) + sphb_mg_download, pinned host buffers; every step's statistics are read on the host, one step behind the launches; bytes are the busiest rank's; median of 3 repetitions",
            "last_step_stats": {"max_speed": last["max_speed"], "max_rho_err": last["max_rho_err"]}}
     release(sim2)
 

@@ -126,6 +126,13 @@ int sphb_step_trace(sphb_ctx *ctx, const float *gravity_xy, int nsteps);
  * the values are those sphb_get_stats would return.  nsteps >= 1. */
 int sphb_step_stats(sphb_ctx *ctx, const float *gravity_xy, int nsteps, sphb_stats *out);
 
+/* The same in two halves, for a host loop that wants the GPU to start step s + 1 while the statistics
+ * of step s are still on their way (the reference hands each frame to a display thread in the same
+ * spirit, :558-579): _begin launches the steps and returns a ticket at once, _end waits for that
+ * ticket's statistics.  At most two tickets may be outstanding; they are collected in order. */
+int sphb_step_stats_begin(sphb_ctx *ctx, const float *gravity_xy, int nsteps, unsigned long long *ticket_out);
+int sphb_step_stats_end(sphb_ctx *ctx, unsigned long long ticket, sphb_stats *out);
+
 /* Copies the state back in ORIGINAL particle order.  Any pointer may be NULL. */
 int sphb_download(sphb_ctx *ctx, sphb_particle *fluid_out, float *du_dt, float *dv_dt);
 int sphb_download_boundary(sphb_ctx *ctx, sphb_particle *boundary_out);

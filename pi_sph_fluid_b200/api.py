@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         "sphb_render": (ci, [vp, vp]),
         "sphb_get_stats": (ci, [vp, vp]),
         "sphb_step_stats": (ci, [vp, vp, ci, vp]),
+        "sphb_step_stats_begin": (ci, [vp, vp, ci, vp]),
+        "sphb_step_stats_end": (ci, [vp, C.c_ulonglong, vp]),
         "sphb_synchronize": (ci, [vp]),
         "sphb_save_state": (ci, [vp, C.c_char_p]),
         "sphb_load_state": (ci, [C.c_char_p, ci, C.POINTER(vp)]),
@@ -282,6 +284,19 @@ class Simulation:
         rc = lib().sphb_step_stats(self._h, g_addr, nsteps, st_ref)
         if rc < 0:
             _check(rc, "sphb_step_stats")
+
+    def step_stats_begin(self, g_addr: int, nsteps: int) -> int:
+        """launches nsteps steps (g_addr as in step_stats_into) and returns the ticket of their statistics"""
+        t = C.c_ulonglong(0)
+        rc = lib().sphb_step_stats_begin(self._h, g_addr, nsteps, C.byref(t))
+        if rc < 0:
+            _check(rc, "sphb_step_stats_begin")
+        return t.value
+
+    def step_stats_end(self, ticket: int, st_ref) -> None:
+        rc = lib().sphb_step_stats_end(self._h, ticket, st_ref)
+        if rc < 0:
+            _check(rc, "sphb_step_stats_end")
 
     def synchronize(self):
         _check(lib().sphb_synchronize(self._h), "sphb_synchronize")

@@ -309,10 +309,12 @@ int sphb_create(const sphb_params *prm, sphb_ctx **out)
     SPHB_CUDA(cudaMemset(c->scan.tile_counter, 0, sizeof(unsigned long long)));
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), 128));
     SPHB_CUDA(cudaMemset(c->d_stats, 0, 128));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_step_slots), (size_t)kStatsSlots * 128));
+    SPHB_CUDA(cudaMemset(c->d_step_slots, 0, (size_t)kStatsSlots * 128));
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats_done), sizeof(unsigned int)));
     SPHB_CUDA(cudaMemset(c->d_stats_done, 0, sizeof(unsigned int)));
-    SPHB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c->h_stats), 256, cudaHostAllocMapped));
-    memset(c->h_stats, 0, 256);
+    SPHB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c->h_stats), 512, cudaHostAllocMapped));     // two slots
+    memset(c->h_stats, 0, 512);
     for (int i = 0; i < 128; i++) SPHB_CUDA(cudaEventCreate(&c->ev[i]));
     SPHB_CUDA(cudaDeviceSynchronize());      // memsets above vs. the non-blocking stream
     *out = c;
@@ -329,7 +331,7 @@ int sphb_destroy(sphb_ctx *c)
     free_set(c->boundary);
     cudaFree(c->d_counters); cudaFree(c->d_gravity); cudaFree(c->d_stage);
     cudaFree(c->d_pixels); cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_l2_scratch);
-    cudaFree(c->scan.tile_state); cudaFree(c->scan.tile_counter); cudaFree(c->d_stats_done);
+    cudaFree(c->scan.tile_state); cudaFree(c->scan.tile_counter); cudaFree(c->d_stats_done); cudaFree(c->d_step_slots);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     for (int i = 0; i < 128; i++) cudaEventDestroy(c->ev[i]);
@@ -439,10 +441,14 @@ int sphb_upload_accel(sphb_ctx *c, const float *du_dt, const float *dv_dt)
 struct StatsBlock { double d[4]; unsigned int u[16]; };     // the 128-byte block k_stats / k_force<STATS> fill
 static void decode_stats(const sphb_ctx *c, const StatsBlock *h, sphb_stats *out);
 
-// stats_out != NULL: the force pass of the LAST step also reduces the step statistics and its last CTA
-// stores them into mapped host memory; the host waits for the sequence word there (no copy, no
-// stream synchronisation).
-static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int nsteps, sphb_stats *stats_out = nullptr)
+// The force pass of the LAST step also reduces the step statistics when the caller asks for them and its
+// last CTA stores them into mapped host memory; the host waits for the sequence word there (no copy, no
+// stream synchronisation).  Two host slots alternate by sequence number, so the statistics of step s can
+// still be on their way while step s + 1 is launched (sphb_step_stats_begin / _end).
+constexpr int kStatsSlotWords = 32;      // 16 block words, the sequence word, padding: 256 bytes per slot
+
+static int step_launch(sphb_ctx *c, float gx, float gy, const float *trace, int nsteps, bool want_stats,
+                       unsigned long long *ticket_out)
 {
     SPHB_ENTER(c);
     if (nsteps < 0) return SPHB_E_ARG;
@@ -450,18 +456,24 @@ static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int ns
     if (!c->accel_ready) { set_error("sphb_compute_accel must run before sphb_step (:604-607 precede :610)"); return SPHB_E_STATE; }
     if (c->mg.on && c->mg.transport != 1 && c->mg.transport != 3) { set_error("slab not connected over NCCL or peer stores: use sphb_mg_group_step"); return SPHB_E_STATE; }
     StepStats ss;
-    if (stats_out && nsteps > 0) {
-        ss.block = reinterpret_cast<unsigned long long *>(c->d_stats);
+    want_stats = want_stats && nsteps > 0;
+    if (want_stats) {
+        if (c->stats_seq - c->stats_collected >= 2) {
+            set_error("two sets of step statistics are outstanding: collect one with sphb_step_stats_end first");
+            return SPHB_E_STATE;
+        }
+        ss.block = c->d_step_slots;
         ss.ctr = c->d_counters;
         ss.flags = c->mg.on ? c->mg.d_flags : nullptr;
         ss.last_id = c->fluid.windowed ? 0xffffffffu : (uint32_t)(c->fluid.n - 1);
         ss.done = c->d_stats_done;
-        ss.host = c->h_stats;
         ss.seq = ++c->stats_seq;
+        ss.host = c->h_stats + kStatsSlotWords * (ss.seq & 1ULL);
+        if (ticket_out) *ticket_out = ss.seq;
     }
     for (int s = 0; s < nsteps; s++) {
         if (trace) { gx = trace[2 * s]; gy = trace[2 * s + 1]; }    // the value every thread reads at :632
-        const bool with_stats = stats_out && s == nsteps - 1;
+        const bool with_stats = want_stats && s == nsteps - 1;
         if (c->mg.on) {
             step_phase_a(c, true);
             int rc = mg_exchange(c);
@@ -473,30 +485,55 @@ static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int ns
         }
         c->steps++;
     }
+    if (want_stats) c->stats_steps[ss.seq & 1ULL] = c->steps;
     SPHB_CUDA(cudaGetLastError());
-    if (stats_out && nsteps > 0) {
-        volatile unsigned long long *seq = c->h_stats + 16;
-        unsigned long long spins = 0;
-        while (*seq != ss.seq) {
-            if ((++spins & 0x3ffULL) == 0) {
-                const cudaError_t q = cudaStreamQuery(c->stream);
-                if (q == cudaSuccess) {
-                    if (*seq == ss.seq) break;
-                    set_error("step statistics were not delivered");
-                    return SPHB_E_STATE;
-                }
-                if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery", __FILE__, __LINE__);
-            }
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
-        }
-        __atomic_thread_fence(__ATOMIC_ACQUIRE);
-        StatsBlock h;
-        memcpy(&h, c->h_stats, sizeof h);
-        decode_stats(c, &h, stats_out);
-    }
     return SPHB_OK;
+}
+
+// waits for the statistics with sequence number `ticket` (the oldest outstanding one) and decodes them
+static int stats_collect(sphb_ctx *c, unsigned long long ticket, sphb_stats *stats_out)
+{
+    if (ticket != c->stats_collected + 1 || ticket > c->stats_seq) {
+        set_error("step statistics are collected in the order they were requested (next: %llu, asked: %llu)",
+                  c->stats_collected + 1, ticket);
+        return SPHB_E_STATE;
+    }
+    const unsigned long long *slot = c->h_stats + kStatsSlotWords * (ticket & 1ULL);
+    volatile const unsigned long long *seq = slot + 16;
+    unsigned long long spins = 0;
+    while (*seq != ticket) {
+        if ((++spins & 0x3ffULL) == 0) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) {
+                if (*seq == ticket) break;
+                set_error("step statistics were not delivered");
+                return SPHB_E_STATE;
+            }
+            if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery", __FILE__, __LINE__);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    StatsBlock h;
+    memcpy(&h, slot, sizeof h);
+    decode_stats(c, &h, stats_out);
+    stats_out->steps = c->stats_steps[ticket & 1ULL];     // the step count when these were requested
+    c->stats_collected = ticket;
+    return SPHB_OK;
+}
+
+static int step_impl(sphb_ctx *c, float gx, float gy, const float *trace, int nsteps, sphb_stats *stats_out = nullptr)
+{
+    if (stats_out && c && c->stats_seq != c->stats_collected) {
+        set_error("step statistics requested with sphb_step_stats_begin are still outstanding");
+        return SPHB_E_STATE;
+    }
+    unsigned long long ticket = 0;
+    int rc = step_launch(c, gx, gy, trace, nsteps, stats_out != nullptr, &ticket);
+    if (rc || !stats_out || nsteps <= 0) return rc;
+    return stats_collect(c, ticket, stats_out);
 }
 
 int sphb_step(sphb_ctx *c, float gx, float gy, int nsteps) { return step_impl(c, gx, gy, nullptr, nsteps); }
@@ -511,6 +548,19 @@ int sphb_step_stats(sphb_ctx *c, const float *gravity_xy, int nsteps, sphb_stats
 {
     if (!out || nsteps < 1 || !gravity_xy) { set_error("sphb_step_stats: needs nsteps >= 1, a gravity sample per step and an output"); return SPHB_E_ARG; }
     return step_impl(c, 0.0f, 0.0f, gravity_xy, nsteps, out);
+}
+
+int sphb_step_stats_begin(sphb_ctx *c, const float *gravity_xy, int nsteps, unsigned long long *ticket_out)
+{
+    if (!ticket_out || nsteps < 1 || !gravity_xy) { set_error("sphb_step_stats_begin: needs nsteps >= 1, a gravity sample per step and a ticket"); return SPHB_E_ARG; }
+    return step_launch(c, 0.0f, 0.0f, gravity_xy, nsteps, true, ticket_out);
+}
+
+int sphb_step_stats_end(sphb_ctx *c, unsigned long long ticket, sphb_stats *out)
+{
+    SPHB_ENTER(c);
+    if (!out) return SPHB_E_ARG;
+    return stats_collect(c, ticket, out);
 }
 
 int sphb_synchronize(sphb_ctx *c)

@@ -34,6 +34,7 @@ constexpr int kStreamThreads = 256;   // advect/bin, reorder, gather/scatter ker
 #define SPHB_MINB_F 8
 #endif
 constexpr int kPairThreads = SPHB_PT;        // density / force CTAs: one thread per particle
+constexpr int kStatsSlots = 64;              // copies of the step-statistics block the force pass spreads its atomics over
 constexpr int kChunkRecWords = 16;           // the record k_density leaves per chunk for k_force (64 bytes)
 constexpr int kListCap = SPHB_LIST_CAP;      // per-thread accepted list entries (u16 tile offsets) before a flush
 constexpr int kTileCap = SPHB_TILE_CAP;      // staged neighbourhood entries per CTA (x 8 B must stay < 64 KiB)
@@ -170,7 +171,8 @@ struct DeviceCounters {        // lives in HBM, read back by sphb_get_stats
 // last CTA to finish stores it, followed by a sequence word, into mapped pinned host memory — the
 // host polls that word, so reading a step's statistics costs no further API call.
 struct StepStats {
-    unsigned long long *block = nullptr;   // device: 16 x 8 bytes (zeroed by the density pass of the step)
+    unsigned long long *block = nullptr;   // device: kStatsSlots x 16 x 8 bytes, all zero between steps (the last
+                                           //   CTA folds and clears them); chunk c adds into slot c % kStatsSlots
     const DeviceCounters *ctr = nullptr;
     const unsigned int *flags = nullptr;   // slabs: [0] lost, [1] overflow
     const uint32_t *id = nullptr;          // original index per sorted slot
@@ -225,10 +227,13 @@ struct sphb_ctx {
     size_t pinned_bytes = 0;
     float2 *d_pixels = nullptr;           // pixel-centre pseudo-particles (:570-577)
     unsigned char *d_frame = nullptr;     // 1 KiB SSD1306 frame
-    double *d_stats = nullptr;            // 4 doubles + 16 words
+    double *d_stats = nullptr;            // 4 doubles + 16 words (sphb_get_stats)
+    unsigned long long *d_step_slots = nullptr;   // StepStats::block
     unsigned int *d_stats_done = nullptr; // StepStats::done
-    unsigned long long *h_stats = nullptr;   // StepStats::host (mapped pinned, 17 words)
-    unsigned long long stats_seq = 0;
+    unsigned long long *h_stats = nullptr;   // StepStats::host (mapped pinned): two slots of 32 words, [0..15] block, [16] sequence
+    unsigned long long stats_seq = 0;        // step statistics requested so far (the sequence word delivered with them)
+    unsigned long long stats_collected = 0;  // ... and read by the host, in order
+    unsigned long long stats_steps[2] = {0, 0};   // sphb_stats::steps of the outstanding requests, by slot
     void *d_l2_scratch = nullptr;         // sphb_flush_l2
     int l2_flush_value = 0;
     bool boundary_ready = false;

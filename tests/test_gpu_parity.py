@@ -358,6 +358,52 @@ def test_step_stats_equals_step_then_get_stats(lib_built, golden075):
     a.close(); b.close()
 
 
+def test_step_stats_pipelined_begin_end(lib_built):
+    """sphb_step_stats_begin / _end: step s + 1 is launched before the statistics of step s are read.
+    Every step's statistics equal those of the blocking call on a second context, the final states are
+    bit-identical, and the ticket rules are enforced (two outstanding at most, collected in order)."""
+    import ctypes
+    pkg = lib_built
+    prm = pkg.default_params(0.01)
+    fluid, boundary = pkg.scene_drop(prm), pkg.scene_boundary(prm)
+    K = 40
+    trace = np.ascontiguousarray([[0.5 * np.sin(0.2 * i), -9.81 + 0.1 * i / K] for i in range(K)], np.float32)
+    with pkg.Simulation(prm) as a, pkg.Simulation(prm) as b:
+        for s in (a, b):
+            s.upload(fluid, boundary); s.init_boundary(); s.compute_accel(*G)
+        ref = [b.step_stats(trace[i:i + 1]) for i in range(K)]
+        st = pkg.Stats()
+        st_ref, addr = ctypes.byref(st), trace.ctypes.data
+        got, prev = [], None
+        for i in range(K):
+            t = a.step_stats_begin(addr + 8 * i, 1)
+            if prev is not None:
+                a.step_stats_end(prev, st_ref)
+                got.append(st.asdict())
+            prev = t
+        # a third request while two are outstanding is refused; so is collecting out of order
+        t2 = a.step_stats_begin(addr, 1)
+        with pytest.raises(pkg.SphbError):
+            a.step_stats_begin(addr, 1)
+        with pytest.raises(pkg.SphbError):
+            a.step_stats_end(t2, st_ref)
+        with pytest.raises(pkg.SphbError):
+            a.step_stats(trace[:1])                  # the blocking form would overtake them
+        a.step_stats_end(prev, st_ref)
+        got.append(st.asdict())
+        a.step_stats_end(t2, st_ref)
+        assert len(got) == K
+        for i, (x, y) in enumerate(zip(got, ref)):
+            for key in ("max_speed", "max_rho", "min_rho", "last_rho_err_ref", "steps", "n_fluid", "max_cell_count"):
+                assert x[key] == y[key], (i, key, x[key], y[key])
+            assert x["kinetic"] == pytest.approx(y["kinetic"], rel=1e-11)
+        b.step_trace(trace[:1])
+        fa, dua, dva = a.download(); fb, dub, dvb = b.download()
+        for fld in FIELDS:
+            assert same_bits(fa[fld], fb[fld]), fld
+        assert same_bits(dua, dub) and same_bits(dva, dvb)
+
+
 def test_step_stats_large_scene(lib_built):
     """Many CTAs (R = 0.01: ~15k particles, >100 chunks): the last-CTA delivery and the per-CTA atomics."""
     prm = lib_built.default_params(0.01)
