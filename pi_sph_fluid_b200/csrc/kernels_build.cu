@@ -50,10 +50,13 @@ __global__ void __launch_bounds__(kStreamThreads)
 k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *__restrict__ vel,
              const float2 *__restrict__ acc, const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellkey,
              uint32_t *__restrict__ key, uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count,
-             DeviceCounters *__restrict__ ctr, const SlabIO io)
+             DeviceCounters *__restrict__ ctr, const SlabIO io, const StepStats deliver)
 {
     pdl_trigger();
     pdl_wait();
+    // sphb_step_stats_begin: the previous step's statistics are summed but not yet with the host; CTA 0
+    // folds and delivers them while the rest of the grid is already advecting
+    if (deliver.block != nullptr && blockIdx.x == 0) stats_fold_deliver(deliver);
     const int n = count_of(cnt);
     const int s = blockIdx.x * kStreamThreads + threadIdx.x;
     bool live = s < n;
@@ -95,14 +98,15 @@ k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *
 }
 
 int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool advect, DeviceCounters *ctr,
-                      const SlabIO *slab)
+                      const SlabIO *slab, const StepStats *deliver)
 {
-    if (ps.n == 0) return 0;
+    const StepStats dl = deliver ? *deliver : StepStats{};
+    if (ps.n == 0) return deliver ? launch_stats_deliver(st, dl) : 0;
     const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
     const uint32_t *keys = ps.sorted ? ps.cellkey : nullptr;
 #define SPHB_ADV(A, S, IO)                                                                                  \
     launch_pdl(st, grid, kStreamThreads, k_advect_bin<A, S>, k, ps.cur(), ps.pos[ps.pc], ps.vel[ps.vc], ps.acc, \
-               ps.id[ps.ic], keys, ps.key, ps.rank, ps.cell_count, ctr, IO)
+               ps.id[ps.ic], keys, ps.key, ps.rank, ps.cell_count, ctr, IO, dl)
     if (slab) { if (advect) SPHB_ADV(true, true, *slab); else SPHB_ADV(false, true, *slab); }
     else { if (advect) SPHB_ADV(true, false, SlabIO()); else SPHB_ADV(false, false, SlabIO()); }
 #undef SPHB_ADV

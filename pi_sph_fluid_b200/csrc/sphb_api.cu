@@ -150,10 +150,10 @@ struct ProfScope {
 // ---- step pieces ----------------------------------------------------------------------
 
 // update_neighbors_context (:104-124) for one set, optionally fused with kick+drift
-int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk)
+int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk, const StepStats *deliver)
 {
     const Consts &k = kk ? *kk : c->k;
-    { ProfScope p(c, SPHB_K_ADVECT_BIN); c->launches += launch_advect_bin(c->stream, k, ps, advect, c->d_counters); }
+    { ProfScope p(c, SPHB_K_ADVECT_BIN); c->launches += launch_advect_bin(c->stream, k, ps, advect, c->d_counters, nullptr, deliver); }
     { ProfScope p(c, SPHB_K_SCAN); c->launches += launch_scan(c->stream, k, ps, c->scan, c->d_counters); }
     { ProfScope p(c, SPHB_K_REORDER); c->launches += launch_reorder(c->stream, k, ps, c->prm.deterministic != 0); }
     return SPHB_OK;
@@ -163,14 +163,14 @@ int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk)
 //   phase A  kick + drift + binning of the resident particles (:615-626); on a slab it also
 //            appends the halo / migration messages for both neighbours
 //   phase B  [slab: bin the received entries] scan, reorder, density+pressure, accelerations, kick
-int step_phase_a(sphb_ctx *c, bool advect)
+int step_phase_a(sphb_ctx *c, bool advect, const StepStats *deliver)
 {
     ProfScope p(c, SPHB_K_ADVECT_BIN);
     if (c->mg.on) {
         const SlabIO io = mg_slab_io(c);
-        c->launches += launch_advect_bin(c->stream, c->k, c->fluid, advect, c->d_counters, &io);
+        c->launches += launch_advect_bin(c->stream, c->k, c->fluid, advect, c->d_counters, &io, deliver);
     } else {
-        c->launches += launch_advect_bin(c->stream, c->k, c->fluid, advect, c->d_counters);
+        c->launches += launch_advect_bin(c->stream, c->k, c->fluid, advect, c->d_counters, nullptr, deliver);
     }
     return SPHB_OK;
 }
@@ -199,7 +199,7 @@ int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kic
         ss_here.id = c->fluid.id[c->fluid.ic];      // the sorted order this step's reorder produced
         ss = &ss_here;
     }
-    { ProfScope p(c, SPHB_K_DENSITY); c->launches += launch_density(c->stream, c->k, c->fluid, c->boundary, c->d_counters, false, true, ss ? ss->block : nullptr); }
+    { ProfScope p(c, SPHB_K_DENSITY); c->launches += launch_density(c->stream, c->k, c->fluid, c->boundary, c->d_counters, false, true, ss ? ss->block : nullptr, ss ? ss->flags : nullptr); }
     { ProfScope p(c, SPHB_K_FORCE); c->launches += launch_force(c->stream, c->k, c->fluid, c->boundary, gx, gy, g_dev, kick2, c->d_counters, true, ss); }
     return SPHB_OK;
 }
@@ -309,8 +309,8 @@ int sphb_create(const sphb_params *prm, sphb_ctx **out)
     SPHB_CUDA(cudaMemset(c->scan.tile_counter, 0, sizeof(unsigned long long)));
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), 128));
     SPHB_CUDA(cudaMemset(c->d_stats, 0, 128));
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_step_slots), (size_t)kStatsSlots * 128));
-    SPHB_CUDA(cudaMemset(c->d_step_slots, 0, (size_t)kStatsSlots * 128));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_step_slots), (size_t)2 * kStatsSlots * 128));      // two sets, by sequence parity
+    SPHB_CUDA(cudaMemset(c->d_step_slots, 0, (size_t)2 * kStatsSlots * 128));
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats_done), sizeof(unsigned int)));
     SPHB_CUDA(cudaMemset(c->d_stats_done, 0, sizeof(unsigned int)));
     SPHB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c->h_stats), 512, cudaHostAllocMapped));     // two slots
@@ -447,8 +447,10 @@ static void decode_stats(const sphb_ctx *c, const StatsBlock *h, sphb_stats *out
 // still be on their way while step s + 1 is launched (sphb_step_stats_begin / _end).
 constexpr int kStatsSlotWords = 32;      // 16 block words, the sequence word, padding: 256 bytes per slot
 
+// defer: the force pass only sums (sphb_step_stats_begin); folding the slots and handing the block to the
+// host is left to CTA 0 of the next advect+bin kernel on the stream, or to stats_collect when none follows.
 static int step_launch(sphb_ctx *c, float gx, float gy, const float *trace, int nsteps, bool want_stats,
-                       unsigned long long *ticket_out)
+                       unsigned long long *ticket_out, bool defer = false)
 {
     SPHB_ENTER(c);
     if (nsteps < 0) return SPHB_E_ARG;
@@ -462,30 +464,37 @@ static int step_launch(sphb_ctx *c, float gx, float gy, const float *trace, int 
             set_error("two sets of step statistics are outstanding: collect one with sphb_step_stats_end first");
             return SPHB_E_STATE;
         }
-        ss.block = c->d_step_slots;
         ss.ctr = c->d_counters;
         ss.flags = c->mg.on ? c->mg.d_flags : nullptr;
         ss.last_id = c->fluid.windowed ? 0xffffffffu : (uint32_t)(c->fluid.n - 1);
-        ss.done = c->d_stats_done;
+        ss.done = defer ? nullptr : c->d_stats_done;
         ss.seq = ++c->stats_seq;
+        // device slots and host slot alternate with the sequence number: request s + 2 reuses what request
+        // s used, and s has been collected by then (two outstanding at most)
+        ss.block = c->d_step_slots + (size_t)(ss.seq & 1ULL) * kStatsSlots * 16;
         ss.host = c->h_stats + kStatsSlotWords * (ss.seq & 1ULL);
         if (ticket_out) *ticket_out = ss.seq;
     }
     for (int s = 0; s < nsteps; s++) {
         if (trace) { gx = trace[2 * s]; gy = trace[2 * s + 1]; }    // the value every thread reads at :632
         const bool with_stats = want_stats && s == nsteps - 1;
+        // statistics a previous sphb_step_stats_begin left undelivered ride on this step's first kernel
+        StepStats pending;
+        const StepStats *deliver = nullptr;
+        if (c->stats_has_pending) { pending = c->stats_pending; deliver = &pending; c->stats_has_pending = false; }
         if (c->mg.on) {
-            step_phase_a(c, true);
+            step_phase_a(c, true, deliver);
             int rc = mg_exchange(c);
             if (rc) return rc;
             step_phase_b(c, gx, gy, true, with_stats ? &ss : nullptr);
         } else {
-            build_grid(c, c->fluid, true);                   // :615-626
+            build_grid(c, c->fluid, true, nullptr, deliver);                   // :615-626
             density_force(c, gx, gy, nullptr, true, with_stats ? &ss : nullptr);         // :630-640
         }
         c->steps++;
     }
     if (want_stats) c->stats_steps[ss.seq & 1ULL] = c->steps;
+    if (want_stats && defer) { c->stats_pending = ss; c->stats_has_pending = true; }
     SPHB_CUDA(cudaGetLastError());
     return SPHB_OK;
 }
@@ -497,6 +506,12 @@ static int stats_collect(sphb_ctx *c, unsigned long long ticket, sphb_stats *sta
         set_error("step statistics are collected in the order they were requested (next: %llu, asked: %llu)",
                   c->stats_collected + 1, ticket);
         return SPHB_E_STATE;
+    }
+    if (c->stats_has_pending && c->stats_pending.seq == ticket) {
+        // no step followed the request: deliver with a kernel of its own
+        c->launches += launch_stats_deliver(c->stream, c->stats_pending);
+        c->stats_has_pending = false;
+        SPHB_CUDA(cudaGetLastError());
     }
     const unsigned long long *slot = c->h_stats + kStatsSlotWords * (ticket & 1ULL);
     volatile const unsigned long long *seq = slot + 16;
@@ -553,7 +568,7 @@ int sphb_step_stats(sphb_ctx *c, const float *gravity_xy, int nsteps, sphb_stats
 int sphb_step_stats_begin(sphb_ctx *c, const float *gravity_xy, int nsteps, unsigned long long *ticket_out)
 {
     if (!ticket_out || nsteps < 1 || !gravity_xy) { set_error("sphb_step_stats_begin: needs nsteps >= 1, a gravity sample per step and a ticket"); return SPHB_E_ARG; }
-    return step_launch(c, 0.0f, 0.0f, gravity_xy, nsteps, true, ticket_out);
+    return step_launch(c, 0.0f, 0.0f, gravity_xy, nsteps, true, ticket_out, true);
 }
 
 int sphb_step_stats_end(sphb_ctx *c, unsigned long long ticket, sphb_stats *out)

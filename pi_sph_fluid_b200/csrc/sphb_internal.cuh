@@ -173,14 +173,88 @@ struct DeviceCounters {        // lives in HBM, read back by sphb_get_stats
 struct StepStats {
     unsigned long long *block = nullptr;   // device: kStatsSlots x 16 x 8 bytes, all zero between steps (the last
                                            //   CTA folds and clears them); chunk c adds into slot c % kStatsSlots
-    const DeviceCounters *ctr = nullptr;
-    const unsigned int *flags = nullptr;   // slabs: [0] lost, [1] overflow
+    const DeviceCounters *ctr = nullptr;   // snapshotted into slot 0 by the density pass of the step
+    const unsigned int *flags = nullptr;   // slabs: [0] lost, [1] overflow (likewise)
     const uint32_t *id = nullptr;          // original index per sorted slot
     uint32_t last_id = 0xffffffffu;        // :657-659 as written reports the LAST particle's error
-    unsigned int *done = nullptr;          // CTAs that have finished (left at zero by the last one)
+    unsigned int *done = nullptr;          // CTAs that have finished (left at zero by the last one); nullptr: the
+                                           //   force pass does not deliver, a later kernel does (stats_fold_deliver)
     unsigned long long *host = nullptr;    // mapped pinned: [0..15] the block, [16] sequence word
     unsigned long long seq = 0;
 };
+
+// Folds the kStatsSlots partial blocks of a step's statistics into one, clears the slots for their next
+// use, and hands the block and then the sequence word to the host through mapped pinned memory.  Run by
+// ONE whole CTA (>= kStatsSlots threads) once every chunk of the force pass has added its sums: the last
+// CTA of the force pass itself (blocking sphb_step_stats), CTA 0 of the next step's advect+bin kernel
+// (sphb_step_stats_begin: the delivery then hides inside that kernel instead of delaying it), or
+// k_stats_deliver when no step follows.  Slot 0 also carries [5 hi] the last particle's rho (:657-659)
+// and, in words 9 and 10, the build / slab counters the density pass of the step snapshotted.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void stats_fold_deliver(const StepStats &ss)
+{
+    __shared__ double s_fd[kStatsSlots / 32][4];
+    __shared__ unsigned int s_fu[kStatsSlots / 32][4];
+    __shared__ unsigned long long s_out[16];
+    __shared__ unsigned long long s_extra[3];
+    const int tid = threadIdx.x;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    unsigned int u0 = 0u, u1 = 0u, u2 = 0u, u4 = 0u;
+    if (tid < kStatsSlots) {
+        unsigned long long *sl = ss.block + (size_t)tid * 16;
+        d0 = __longlong_as_double((long long)__ldcg(sl + 0)); d1 = __longlong_as_double((long long)__ldcg(sl + 1));
+        d2 = __longlong_as_double((long long)__ldcg(sl + 2)); d3 = __longlong_as_double((long long)__ldcg(sl + 3));
+        const unsigned long long w4 = __ldcg(sl + 4), w5 = __ldcg(sl + 5), w6 = __ldcg(sl + 6);
+        u0 = (unsigned int)w4; u1 = (unsigned int)(w4 >> 32);
+        u2 = (unsigned int)w5;
+        u4 = (unsigned int)w6;
+        if (tid == 0) { s_extra[0] = w5 >> 32; s_extra[1] = __ldcg(sl + 9); s_extra[2] = __ldcg(sl + 10); }
+#pragma unroll
+        for (int i = 0; i < 16; i++) sl[i] = 0ULL;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            d0 += __shfl_xor_sync(0xffffffffu, d0, d); d1 += __shfl_xor_sync(0xffffffffu, d1, d);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, d); d3 += __shfl_xor_sync(0xffffffffu, d3, d);
+        }
+        u0 = __reduce_max_sync(0xffffffffu, u0); u1 = __reduce_max_sync(0xffffffffu, u1);
+        u2 = __reduce_max_sync(0xffffffffu, u2); u4 = __reduce_add_sync(0xffffffffu, u4);
+        if ((tid & 31) == 0) {
+            const int w = tid >> 5;
+            s_fd[w][0] = d0; s_fd[w][1] = d1; s_fd[w][2] = d2; s_fd[w][3] = d3;
+            s_fu[w][0] = u0; s_fu[w][1] = u1; s_fu[w][2] = u2; s_fu[w][3] = u4;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        unsigned int m0 = 0u, m1 = 0u, m2 = 0u, c4 = 0u;
+#pragma unroll
+        for (int w = 0; w < kStatsSlots / 32; w++) {
+            a0 += s_fd[w][0]; a1 += s_fd[w][1]; a2 += s_fd[w][2]; a3 += s_fd[w][3];
+            m0 = s_fu[w][0] > m0 ? s_fu[w][0] : m0; m1 = s_fu[w][1] > m1 ? s_fu[w][1] : m1;
+            m2 = s_fu[w][2] > m2 ? s_fu[w][2] : m2; c4 += s_fu[w][3];
+        }
+        // the 128-byte block of sphb_get_stats: 4 doubles | u32 [0] max speed [1] key(max rho) [2] ~key(min rho)
+        // [3] last particle's rho [4] owned [5] escaped [6] max cell population [7] lost [8] overflow
+        s_out[0] = (unsigned long long)__double_as_longlong(a0); s_out[1] = (unsigned long long)__double_as_longlong(a1);
+        s_out[2] = (unsigned long long)__double_as_longlong(a2); s_out[3] = (unsigned long long)__double_as_longlong(a3);
+        s_out[4] = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+        s_out[5] = (unsigned long long)m2 | (s_extra[0] << 32);
+        s_out[6] = (unsigned long long)c4 | ((s_extra[1] & 0xffffffffULL) << 32);
+        s_out[7] = (s_extra[1] >> 32) | ((s_extra[2] & 0xffffffffULL) << 32);
+        s_out[8] = s_extra[2] >> 32;
+#pragma unroll
+        for (int i = 9; i < 16; i++) s_out[i] = 0ULL;
+    }
+    __syncthreads();
+    if (tid < 16) {
+        ss.host[tid] = s_out[tid];
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile unsigned long long *>(ss.host + 16) = ss.seq;
+}
+#endif
 
 // Multi-GPU slab state of one rank (sphb_mg.cu)
 struct MgState {
@@ -234,6 +308,8 @@ struct sphb_ctx {
     unsigned long long stats_seq = 0;        // step statistics requested so far (the sequence word delivered with them)
     unsigned long long stats_collected = 0;  // ... and read by the host, in order
     unsigned long long stats_steps[2] = {0, 0};   // sphb_stats::steps of the outstanding requests, by slot
+    sphb::StepStats stats_pending;            // sphb_step_stats_begin: statistics summed on the device but not yet
+    bool stats_has_pending = false;           //   folded and delivered (the next advect+bin kernel or the collect does it)
     void *d_l2_scratch = nullptr;         // sphb_flush_l2
     int l2_flush_value = 0;
     bool boundary_ready = false;
@@ -263,7 +339,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 // ---- kernel launchers (kernels_build.cu) ---------------------------------------------------
 // All launch on `st`; return the number of kernels launched.
 int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool advect, DeviceCounters *ctr,
-                      const SlabIO *slab = nullptr);
+                      const SlabIO *slab = nullptr, const StepStats *deliver = nullptr);
+int launch_stats_deliver(cudaStream_t st, const StepStats &ss);
 int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const SlabIO &slab, DeviceCounters *ctr);
 int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc, DeviceCounters *ctr);
 int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deterministic);
@@ -279,7 +356,7 @@ int launch_cell_ids(cudaStream_t st, const Consts &k, const ParticleSet &ps, int
 int launch_pseudomass(cudaStream_t st, const Consts &k, ParticleSet &boundary);
 int launch_density(cudaStream_t st, const Consts &k, ParticleSet &fluid, const ParticleSet &boundary,
                    DeviceCounters *ctr, bool count_pairs, bool allow_stage = true,
-                   unsigned long long *stats_zero = nullptr);
+                   unsigned long long *stats_zero = nullptr, const unsigned int *stats_flags = nullptr);
 int launch_force(cudaStream_t st, const Consts &k, ParticleSet &fluid, const ParticleSet &boundary,
                  float gx, float gy, const float2 *g_dev, bool kick2, DeviceCounters *ctr,
                  bool allow_stage = true, const StepStats *stats = nullptr);
@@ -297,8 +374,8 @@ int launch_tait_aos(cudaStream_t st, const Consts &k, int n, sphb_particle *aos)
 // ---- host-side helpers (sphb_api.cu) ---------------------------------------------------------
 int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_mass);
 int ensure_stage(sphb_ctx *c, size_t bytes);
-int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk = nullptr);
-int step_phase_a(sphb_ctx *c, bool advect);
+int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk = nullptr, const StepStats *deliver = nullptr);
+int step_phase_a(sphb_ctx *c, bool advect, const StepStats *deliver = nullptr);
 int step_phase_b(sphb_ctx *c, float gx, float gy, bool kick2, const StepStats *ss = nullptr);
 int free_set_public(ParticleSet &ps);
 
