@@ -25,7 +25,7 @@ def main():
     dev = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
-    R, steps, g = 0.01, 400, (60.0, -9.81)     # strong sideways pull: particles cross the cuts
+    R, steps, g = 0.01, 600, (200.0, -9.81)    # strong sideways pull: particles cross the cuts (counted below)
     prm = pkg.default_params(R, device=dev)
     box = (2 * R, 1.5, 2 * R, 0.6)
     cuts = pkg.plan_cuts(pkg.scene_block_column_hist(prm, *box), world)
@@ -49,7 +49,7 @@ def main():
     st = slab.allreduce_stats()
     info = slab.info()
     gathered = [None] * world
-    dist.all_gather_object(gathered, (ids, f, du, dv))
+    dist.all_gather_object(gathered, (ids, f, du, dv, base, len(part)))
     ok = True
     if rank == 0:
         full = pkg.scene_block(prm, *box)
@@ -59,8 +59,10 @@ def main():
             rst = sim.stats()
         out = np.zeros(len(full), pkg.PARTICLE); odu = np.zeros(len(full), np.float32); odv = np.zeros(len(full), np.float32)
         seen = np.zeros(len(full), np.int32)
-        for i, ff, a, b in gathered:
+        migrated = 0
+        for i, ff, a, b, base_r, n_r in gathered:
             out[i] = ff; odu[i] = a; odv[i] = b; seen[i] += 1
+            migrated += int(((i < base_r) | (i >= base_r + n_r)).sum())      # owned now, uploaded elsewhere
         ok = bool((seen == 1).all())
         for fld in out.dtype.names:
             ok &= bool(np.array_equal(out[fld].view("u4"), rf[fld].view("u4")))
@@ -68,8 +70,9 @@ def main():
         ok &= st["n_fluid"] == len(full) and st["n_lost"] == 0 and st["n_overflow"] == 0
         ok &= abs(st["kinetic"] - rst["kinetic"]) <= 1e-9 * abs(rst["kinetic"]) and st["max_speed"] == rst["max_speed"]
         moved = sum(int(((pkg.columns_of(prm, ff["x"]) < cuts[r]) | (pkg.columns_of(prm, ff["x"]) >= cuts[r + 1])).sum())
-                    for r, (i, ff, a, b) in enumerate(gathered))
-        print(f"world {world} ({transport}): {len(full)} particles, {steps} steps, owned-out-of-slab {moved}, "
+                    for r, (i, ff, a, b, _b, _n) in enumerate(gathered))
+        ok &= migrated > 0 or world == 1
+        print(f"world {world} ({transport}): {len(full)} particles, {steps} steps, migrated {migrated}, owned-out-of-slab {moved}, "
               f"message {info['message_bytes']} B, sent {info['bytes_sent']} B, identical={ok}")
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{dev}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
