@@ -80,7 +80,8 @@ typedef struct sphb_stats {
     unsigned int n_fluid, n_boundary; /* on a slab context: particles this rank owns / keeps */
     unsigned long long steps;
     unsigned int n_lost;            /* slabs: particles that moved > 2 cell columns in one step  */
-    unsigned int n_overflow;        /* slabs: halo message or slot capacity exceeded (fatal)     */
+    unsigned int n_overflow;        /* slabs: halo message or slot capacity exceeded (fatal);    */
+                                    /*   bit 30: a neighbour's message did not arrive in 20 s    */
 } sphb_stats;
 
 typedef struct sphb_ctx sphb_ctx;

@@ -181,9 +181,12 @@ k_bin_recv(const Consts k, const SlabIO io, const int *__restrict__ n_cur, int *
             if (io.has[side]) {
                 const uint32_t *h = io.recv[side].hdr();
                 const unsigned long long t0 = global_timer_ns();
+                // a slab that has timed out once stays flagged and does not wait again (the run is lost
+                // either way; it should end quickly rather than after one time-out per step)
+                const bool given_up = (*reinterpret_cast<volatile unsigned int *>(io.overflow) & kHaloTimeoutFlag) != 0u;
                 bool ok;
                 while (!(ok = ld_acquire_sys_u32(h + 1) == io.wait_epoch)) {
-                    if (global_timer_ns() - t0 > kHaloWaitNs) break;
+                    if (given_up || global_timer_ns() - t0 > kHaloWaitNs) break;
                     __nanosleep(100);
                 }
                 if (ok) c = ld_acquire_sys_u32(h);
