@@ -422,11 +422,27 @@ def run_gpu(args, spec, rank, world):
                    "warm_l2_value": total_particles * K / (warm_ms * 1e-3),
                    "timing": "CUDA events on the library stream around each step; max over ranks",
                    "wall_s_timed_region": round(t_wall, 4),
+                   "scaling_note": scaling_note(),
                    "build": pkg.lib().sphb_build_info().decode()},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     sim.close()
     return line
+
+
+def scaling_note():
+    """The N = 1 line runs BASELINE configs[1] (262k particles), the N > 1 lines 8M particles per GPU:
+    the number to hold an N-GPU line against is the same 8M-particle load on ONE GPU, measured with
+    `bench.py --workload dam8m` and committed under profiles/."""
+    note = {"per_gpu_load_at_n_gt_1": "dam break, 8M particles per GPU (N = 8: BASELINE configs[3], 64M)",
+            "n1_workload": "BASELINE configs[1], 262,204 particles (latency-bound: 6 kernels of ~10 us)"}
+    try:
+        files = sorted((ROOT / "profiles").glob("r*_bench_dam8m*.json"))
+        j = json.loads(files[-1].read_text().strip().splitlines()[-1])
+        note["one_gpu_on_8m_particles"] = {"value": j["value"], "ms_per_step": j["ms_per_step"], "source": f"profiles/{files[-1].name}"}
+    except Exception:
+        pass
+    return note
 
 
 def run_gpu_slabs(args, spec, rank, world):
@@ -651,6 +667,7 @@ def run_gpu_slabs(args, spec, rank, world):
                    "timing": "CUDA events on the library stream around the K steps, barrier + synchronize both sides; max over ranks",
                    "wall_s_timed_region": round(t_wall, 4),
                    "merged_stats": {k2: st[k2] for k2 in ("n_fluid", "n_lost", "n_overflow", "n_escaped", "max_speed", "max_rho_err")},
+                   "scaling_note": scaling_note(),
                    "build": pkg.lib().sphb_build_info().decode()},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
