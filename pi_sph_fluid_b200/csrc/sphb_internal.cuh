@@ -10,7 +10,10 @@
 namespace sphb {
 
 // ---- tunables ----------------------------------------------------------------------------
-constexpr int kStreamThreads = 256;   // advect/bin, reorder, gather/scatter kernels
+#ifndef SPHB_STREAM_THREADS
+#define SPHB_STREAM_THREADS 256
+#endif
+constexpr int kStreamThreads = SPHB_STREAM_THREADS;   // advect/bin, reorder, gather/scatter kernels
 // (the SPHB_* macros exist so that scripts/tune_pair.sh can build variants; defaults are the tuned values)
 #ifndef SPHB_PT
 #define SPHB_PT 128
