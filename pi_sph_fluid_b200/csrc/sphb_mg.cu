@@ -364,7 +364,7 @@ int sphb_mg_disconnect_ipc(sphb_ctx *c)
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
     for (int side = 0; side < 2; side++)
         if (m.ipc_peer_block[side]) { SPHB_CUDA(cudaIpcCloseMemHandle(m.ipc_peer_block[side])); m.ipc_peer_block[side] = nullptr; }
-    m.transport = m.nccl_comm ? 1 : 0;
+    m.transport = (m.nccl_comm || m.world == 1) ? 1 : 0;      // back to what sphb_mg_configure / _connect_nccl left
     return SPHB_OK;
 }
 
