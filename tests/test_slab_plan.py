@@ -78,12 +78,13 @@ def test_merge_stats(lib_built):
     assert (out.mass, out.n_fluid, out.max_rho, out.min_rho, out.max_speed, out.n_lost) == (3.0, 15, 1003.0, 990.0, 2.0, 3)
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 3])
 def test_halo_and_migration_protocol_over_gloo(lib_built, oracle_built, tmp_path, world):
-    """world_size-2 gloo job: each rank runs the slab protocol on the host with the oracle as the
-    physics; the union of the owned particles must equal the oracle's single-domain run bit for bit."""
-    R, steps, g = 0.03, 120, (300.0, -9.81)      # huge sideways pull: particles cross the cut
-    port = 29650
+    """world_size-2 and -3 gloo jobs (the middle rank of three has two neighbours): each rank runs the
+    slab protocol on the host with the oracle as the physics; the union of the owned particles must
+    equal the oracle's single-domain run bit for bit."""
+    R, steps, g = 0.03, 120, (300.0, -9.81)      # huge sideways pull: particles cross the cuts
+    port = 29650 + 7 * world
     procs = [subprocess.Popen([sys.executable, str(ROOT / "tests" / "slab_emul.py"), str(r), str(world), str(port),
                                str(R), str(steps), str(g[0]), str(g[1]), str(tmp_path)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
