@@ -179,8 +179,8 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_scene(pkg, spec, deterministic=True, device=0):
-    prm = pkg.default_params(spec["R"], deterministic=deterministic, device=device)
+def build_scene(pkg, spec, deterministic=True, device=0, fast_force=False):
+    prm = pkg.default_params(spec["R"], deterministic=deterministic, device=device, fast_force=fast_force)
     if spec["scene"] == "drop":
         fluid = pkg.scene_drop(prm)
     elif "box" in spec:
@@ -277,7 +277,8 @@ def run_gpu(args, spec, rank, world):
 
     dev = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(dev)
-    prm, fluid, boundary = build_scene(pkg, spec, deterministic=not args.nondeterministic, device=dev)
+    prm, fluid, boundary = build_scene(pkg, spec, deterministic=not args.nondeterministic, device=dev,
+                                       fast_force=args.fast_force)
     n = len(fluid)
     K, W = args.steps, max(args.warmup, 3)
 
@@ -455,7 +456,7 @@ def run_gpu_slabs(args, spec, rank, world):
     dev = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(dev)
     R = spec["R"]
-    prm = pkg.default_params(R, deterministic=not args.nondeterministic, device=dev)
+    prm = pkg.default_params(R, deterministic=not args.nondeterministic, device=dev, fast_force=args.fast_force)
     if "box" in spec:
         box = spec["box"]
     else:
@@ -685,6 +686,9 @@ def main():
     ap.add_argument("--nondeterministic", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg")
+    ap.add_argument("--fast-force", action="store_true",
+                    help="sphb_params.fast_force = 1: the single-precision force arithmetic (outside the 1e-4 parity bar "
+                         "at >= 4M particles) instead of the reference's own (default, bit-identical accelerations)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))

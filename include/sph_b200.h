@@ -64,7 +64,16 @@ typedef struct sphb_params {
                               reproducible.  0: in-cell order is whatever the atomic
                               counting sort produced.                              */
     int device;         /* CUDA device ordinal                                    */
-    int reserved[6];
+    int fast_force;     /* 0 (default): calculate_accelerations (:303-373) in the reference's own
+                              arithmetic — float/double types, operation order and roundings of
+                              :317-337, :52-62, :219-228 — so du_dt, dv_dt are bit-identical with
+                              the reference's source semantics (deterministic = 1).
+                           1: single precision throughout with approximate rsqrt / reciprocal
+                              and folded constants: ~1.8x faster force pass, acceleration within
+                              1e-4*max(|a|, G) of the reference up to ~1M particles only (the
+                              artificial-pressure pair terms grow like 1/H and so does their
+                              rounding noise: 3.6e-4*G at 4M particles).                  */
+    int reserved[5];
 } sphb_params;
 
 typedef struct sphb_stats {
@@ -168,6 +177,15 @@ int sphb_grid_shape(sphb_ctx *ctx, int *n_cells_rows, int *m_cells_cols);
  * indices in this library's visiting order (== the reference's order when
  * deterministic = 1).  Returns the number of particles whose count exceeded cap. */
 int sphb_neighbor_lists(sphb_ctx *ctx, int which, int cap, int *counts, int *lists);
+
+/* The pair term m_j*temp_ij*grad_a W_ij of calculate_accelerations (:317-337, :52-62, :226) for n
+ * caller-given pairs, one device thread per pair — the device instruction sequences of the force pass
+ * made testable one pair at a time.  pairs: 12 floats each (x_i y_i x_j y_j | u_i v_i u_j v_j |
+ * rho_i p_i/rho_i^2 rho_j p_j/rho_j^2), m_j = the uniform fluid mass; out: (tx, ty) per pair.
+ * variant 0: the hot loop's form (packed, exact-division shortcuts), 1: general IEEE divisions,
+ * 2: scalar form with the shortcuts; +4: j is a boundary particle (:346-365).  *exact_shortcuts says
+ * whether the host verified the shortcuts for this context's H (variants 0, 2 are only then exact). */
+int sphb_probe_force_pair(sphb_ctx *ctx, int n, const float *pairs, int variant, float *out_txy, int *exact_shortcuts);
 
 /* ---- measurement hooks --------------------------------------------------------------- */
 

@@ -34,7 +34,7 @@ class Params(C.Structure):
         ("vol", C.c_float),
         ("x_min", C.c_float), ("x_max", C.c_float), ("y_min", C.c_float), ("y_max", C.c_float),
         ("cell_length", C.c_float), ("deterministic", C.c_int), ("device", C.c_int),
-        ("reserved", C.c_int * 6),
+        ("fast_force", C.c_int), ("reserved", C.c_int * 5),
     ]
 
 
@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         "sphb_profile": (ci, [vp, ci]),
         "sphb_profile_read": (ci, [vp, vp, vp, ci]),
         "sphb_pair_stats": (ci, [vp, vp, vp]),
+        "sphb_probe_force_pair": (ci, [vp, ci, vp, ci, vp, vp]),
         "sphb_flush_l2": (ci, [vp]),
         "sphb_stream": (vp, [vp]),
         "sphb_launch_count": (C.c_ulonglong, [vp]),
@@ -169,11 +170,12 @@ def _particles(a: np.ndarray) -> np.ndarray:
 
 
 def default_params(R: float = 0.075, width: float = 4.0, height: float = 2.0,
-                   deterministic: bool = True, device: int = 0) -> Params:
+                   deterministic: bool = True, device: int = 0, fast_force: bool = False) -> Params:
     prm = Params()
     _check(lib().sphb_default_params(C.byref(prm), R, width, height), "sphb_default_params")
     prm.deterministic = int(deterministic)
     prm.device = device
+    prm.fast_force = int(fast_force)
     return prm
 
 
@@ -355,6 +357,14 @@ class Simulation:
         lists = np.zeros((n, cap), np.int32)
         over = _check(lib().sphb_neighbor_lists(self._h, which, cap, _p(counts), _p(lists)), "sphb_neighbor_lists")
         return counts, lists, over
+
+    def probe_force_pair(self, pairs: np.ndarray, variant: int = 0):
+        """sphb_probe_force_pair: (n, 12) float32 pairs -> ((n, 2) float32 pair terms, shortcuts verified?)."""
+        pairs = np.ascontiguousarray(pairs, np.float32).reshape(-1, 12)
+        out = np.zeros((len(pairs), 2), np.float32)
+        ok = C.c_int(0)
+        _check(lib().sphb_probe_force_pair(self._h, len(pairs), _p(pairs), variant, _p(out), C.byref(ok)), "sphb_probe_force_pair")
+        return out, bool(ok.value)
 
     def pair_stats(self):
         c, a = C.c_double(), C.c_double()

@@ -21,13 +21,27 @@ inline float host_W(float H, float r)
     return nf * powf(a, 4) * b;
 }
 
+// the same with powf(a, 4) as the multiply chain gcc emits under the reference's shipped -Ofast — the flavour
+// the kernels follow; W_ref of the STRICT force pass
+inline float host_W_chain(float H, float r)
+{
+    const float nf = (float)(7 / (4 * M_PI * (double)H * (double)H));
+    const float q = r / H;
+    const float a = 1 - 0.5f * q, b = 1 + 2 * q;
+    const float a2 = a * a;
+    return nf * (a2 * a2) * b;
+}
+
 // Is  q0 = r*y, q = q0 + fma(-q0, H, r)*y  (y = RN(1/H)) the correctly rounded r/H for every r?
 // The expression is invariant under scaling r by 2, so all 2^23 mantissas of one binade decide it.
+// (Serves any constant divisor: H and W_ref.)
 inline bool markstein_div_exact(float H)
 {
-    static float cached_H = 0.0f;
-    static bool cached = false;
-    if (H == cached_H) return cached;
+    static float cached_H[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    static bool cached[4] = {false, false, false, false};
+    static int next = 0;
+    for (int i = 0; i < 4; i++)
+        if (H == cached_H[i]) return cached[i];
     const float y = 1.0f / H;
     bool ok = true;
     for (unsigned m = 0; m < (1u << 23) && ok; m++) {
@@ -38,8 +52,9 @@ inline bool markstein_div_exact(float H)
         const float q = fmaf(fmaf(-q0, H, r), y, q0);
         ok = (q == r / H);
     }
-    cached_H = H;
-    cached = ok;
+    cached_H[next] = H;
+    cached[next] = ok;
+    next = (next + 1) & 3;
     return ok;
 }
 
@@ -73,6 +88,18 @@ inline Consts make_consts(const sphb_params &p, float uniform_mass)
     k.b_c = (float)(2.0 / Hd);
     k.art_c = (float)(pow(0.1, 0.25) * (double)k.nf * (double)k.inv_W_ref);
     k.div_exact = markstein_div_exact(p.H) ? 1 : 0;
+    k.W_ref = host_W_chain(p.H, (float)(0.2 * Hd));               // :325, W(0.2*H, 0, 0, 0)
+    k.inv_W_ref_c = 1.0f / k.W_ref;
+    k.wref_div_exact = markstein_div_exact(k.W_ref) ? 1 : 0;
+    k.nf_m5 = k.nf * (-5);                                        // :56
+    k.eps_h2_d = 0.01 * Hd * Hd;                                  // :332
+    k.visc_c_d = -0.01 * (double)p.c0;                            // :334
+    {
+        int e;
+        const double mant = frexp(fabs(k.visc_c_d), &e);
+        k.visc_pow2 = (mant == 0.5) ? 1 : 0;
+        k.visc_c_f = (float)k.visc_c_d;
+    }
     {   // corner-cell culling radius: 2H plus 8 ulp of the largest coordinate (covers the rounding
         // of cell edges and offsets), squared, rounded up
         const float big = fmaxf(fmaxf(fabsf(p.x_min), fabsf(p.x_max)), fmaxf(fabsf(p.y_min), fabsf(p.y_max)));

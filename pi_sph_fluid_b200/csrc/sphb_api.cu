@@ -200,7 +200,7 @@ int density_force(sphb_ctx *c, float gx, float gy, const float2 *g_dev, bool kic
         ss = &ss_here;
     }
     { ProfScope p(c, SPHB_K_DENSITY); c->launches += launch_density(c->stream, c->k, c->fluid, c->boundary, c->d_counters, false, true, ss ? ss->block : nullptr, ss ? ss->flags : nullptr); }
-    { ProfScope p(c, SPHB_K_FORCE); c->launches += launch_force(c->stream, c->k, c->fluid, c->boundary, gx, gy, g_dev, kick2, c->d_counters, true, ss); }
+    { ProfScope p(c, SPHB_K_FORCE); c->launches += launch_force(c->stream, c->k, c->fluid, c->boundary, gx, gy, g_dev, kick2, c->d_counters, true, ss, c->prm.fast_force != 0); }
     return SPHB_OK;
 }
 
@@ -672,6 +672,27 @@ int sphb_neighbor_lists(sphb_ctx *c, int which, int cap, int *counts, int *lists
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
     SPHB_CUDA(cudaMemsetAsync(d_over, 0, sizeof(unsigned int), c->stream));
     return (int)over;
+}
+
+int sphb_probe_force_pair(sphb_ctx *c, int n, const float *pairs, int variant, float *out_txy, int *exact_shortcuts)
+{
+    SPHB_ENTER(c);
+    if (n < 0 || (n > 0 && (!pairs || !out_txy)) || variant < 0 || variant > 6) return SPHB_E_ARG;
+    if (exact_shortcuts) *exact_shortcuts = (c->k.div_exact && c->k.wref_div_exact && c->k.visc_pow2) ? 1 : 0;
+    if (n == 0) return SPHB_OK;
+    const size_t ib = (size_t)n * 12 * sizeof(float), ob = (size_t)n * 2 * sizeof(float);
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    int rc = ensure_stage(c, ib + ob + 64);
+    if (rc) return rc;
+    float *d_in = static_cast<float *>(c->d_stage), *d_out = d_in + (size_t)n * 12;
+    SPHB_CUDA(cudaMemcpyAsync(d_in, pairs, ib, cudaMemcpyHostToDevice, c->stream));
+    Consts k = c->k;
+    if (c->fluid.n == 0) k.mass = c->prm.rho0 * c->prm.vol;
+    c->launches += launch_probe_force_pair(c->stream, k, n, d_in, variant, d_out);
+    SPHB_CUDA(cudaMemcpyAsync(out_txy, d_out, ob, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
 }
 
 int sphb_pair_stats(sphb_ctx *c, double *cand, double *acc)

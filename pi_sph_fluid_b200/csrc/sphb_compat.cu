@@ -225,7 +225,7 @@ void calculate_accelerations(float *du_dt_fluid, float *dv_dt_fluid, struct part
     const unsigned int moved = refresh(ctx_fluid, reinterpret_cast<sphb_particle *>(fluid), where);
     refresh(ctx_boundary, reinterpret_cast<sphb_particle *>(boundary), where);
     c->launches += launch_force(c->stream, c->k, c->fluid, ctx_boundary->core->fluid, gravity_x, gravity_y, nullptr,
-                                false, c->d_counters, moved == 0);
+                                false, c->d_counters, moved == 0, nullptr, c->prm.fast_force != 0);
     const int n = ctx_fluid->n_particles;
     if (ensure_stage(c, (size_t)n * (sizeof(sphb_particle) + 2 * sizeof(float)) + 64)) die(where);
     float *d_du = static_cast<float *>(c->d_stage), *d_dv = d_du + n;

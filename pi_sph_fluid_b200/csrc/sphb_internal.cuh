@@ -36,6 +36,9 @@ constexpr int kStreamThreads = SPHB_STREAM_THREADS;   // advect/bin, reorder, ga
 #ifndef SPHB_MINB_F
 #define SPHB_MINB_F 8
 #endif
+#ifndef SPHB_MINB_FS
+#define SPHB_MINB_FS 8      // the reference-arithmetic force pass (k_force MODE 1 / 2)
+#endif
 constexpr int kPairThreads = SPHB_PT;        // density / force CTAs: one thread per particle
 constexpr int kStatsSlots = 64;              // copies of the step-statistics block the force pass spreads its atomics over
 constexpr int kChunkRecWords = 16;           // the record k_density leaves per chunk for k_force (64 bytes)
@@ -362,7 +365,8 @@ int launch_density(cudaStream_t st, const Consts &k, ParticleSet &fluid, const P
                    unsigned long long *stats_zero = nullptr, const unsigned int *stats_flags = nullptr);
 int launch_force(cudaStream_t st, const Consts &k, ParticleSet &fluid, const ParticleSet &boundary,
                  float gx, float gy, const float2 *g_dev, bool kick2, DeviceCounters *ctr,
-                 bool allow_stage = true, const StepStats *stats = nullptr);
+                 bool allow_stage = true, const StepStats *stats = nullptr, bool fast_force = false);
+int launch_probe_force_pair(cudaStream_t st, const Consts &k, int n, const float *in, int variant, float *out);
 int launch_neighbor_lists(cudaStream_t st, const Consts &k, const ParticleSet &a, const ParticleSet &b,
                           bool same, int cap, int *counts, int *lists, unsigned int *overflow);
 

@@ -80,3 +80,10 @@ def bits(a):
 
 def same_bits(a, b) -> bool:
     return np.array_equal(bits(a), bits(b))
+
+
+def same_bits_nan(a, b) -> bool:
+    """Bit-for-bit, any NaN equal to any NaN (0/0 is 0xFFC00000 on x86 and 0x7FFFFFFF on the GPU)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(bits(a)[~na], bits(b)[~nb])

@@ -113,12 +113,21 @@ void emu_compute_accel(const sphb_params *prm, sphb_particle *f, int n, const sp
         f[i].p = tait_pressure(k, rho);
         prr[i] = p_over_rho2(f[i].p, rho);
     }
+    const bool fast = prm->fast_force != 0;
     for (int i = 0; i < n; i++) {
         float sx = 0, sy = 0, bx = 0, by = 0;
         for_each_candidate(k, f[i].x, f[i].y, sf, [&](int j) {
             const float dx = f_sub(f[i].x, f[j].x), dy = f_sub(f[i].y, f[j].y);
             const float d2 = dist2(dx, dy);
             if (within_support(k, d2) && j != i) {
+                if (!fast) {      // k_force MODE 1 / 2: the reference's arithmetic (:317-337, :52-62, :219-228)
+                    const float xu = f_add(f_mul(dx, f_sub(f[i].u, f[j].u)), f_mul(dy, f_sub(f[i].v, f[j].v)));
+                    const PairStrict o = force_pair_strict<true, false, false>(k, dx, dy, d2, xu, prr[i], prr[j], f[i].rho,
+                                                                               f[j].rho, f[j].m);
+                    sx = f_add(sx, o.tx);
+                    sy = f_add(sy, o.ty);
+                    return;
+                }
                 const float xu = dx * (f[i].u - f[j].u) + dy * (f[i].v - f[j].v);
                 const float tg = f[j].m * force_pair(k, d2, xu, prr[i] + prr[j], f[i].rho + f[j].rho);
                 sx += tg * dx;
@@ -130,14 +139,27 @@ void emu_compute_accel(const sphb_params *prm, sphb_particle *f, int n, const sp
                 const float dx = f_sub(f[i].x, b[j].x), dy = f_sub(f[i].y, b[j].y);
                 const float d2 = dist2(dx, dy);
                 if (within_support(k, d2)) {
+                    if (!fast) {
+                        const float xu = f_add(f_mul(dx, f_sub(f[i].u, b[j].u)), f_mul(dy, f_sub(f[i].v, b[j].v)));
+                        const PairStrict o = force_pair_strict<false, false, false>(k, dx, dy, d2, xu, prr[i], 0.0f, f[i].rho,
+                                                                                    0.0f, b[j].m);
+                        bx = f_add(bx, o.tx);
+                        by = f_add(by, o.ty);
+                        return;
+                    }
                     const float xu = dx * (f[i].u - b[j].u) + dy * (f[i].v - b[j].v);
                     const float tg = b[j].m * force_pair(k, d2, xu, prr[i], f[i].rho + f[i].rho);
                     bx += tg * dx;
                     by += tg * dy;
                 }
             });
-        du[i] = (gx - k.grad_c * sx) - k.grad_c * bx;
-        dv[i] = (gy - k.grad_c * sy) - k.grad_c * by;
+        if (!fast) {
+            du[i] = f_sub(f_sub(gx, sx), bx);      // :370
+            dv[i] = f_sub(f_sub(gy, sy), by);      // :371
+        } else {
+            du[i] = (gx - k.grad_c * sx) - k.grad_c * bx;
+            dv[i] = (gy - k.grad_c * sy) - k.grad_c * by;
+        }
     }
 }
 
@@ -158,6 +180,22 @@ void emu_step(const sphb_params *prm, sphb_particle *f, int n, const sphb_partic
             f[i].u = kick(k, f[i].u, du[i]);
             f[i].v = kick(k, f[i].v, dv[i]);
         }
+    }
+}
+
+// the pair term of the force pass for caller-given pairs (layout of sphb_probe_force_pair)
+void emu_force_pair(const sphb_params *prm, int n, const float *in, int boundary, float *out)
+{
+    const Consts k = make_consts(*prm, prm->rho0 * prm->vol);
+    for (int i = 0; i < n; i++) {
+        const float *a = in + (size_t)i * 12;
+        const float dx = f_sub(a[0], a[2]), dy = f_sub(a[1], a[3]);
+        const float d2 = dist2(dx, dy);
+        const float xu = f_add(f_mul(dx, f_sub(a[4], a[6])), f_mul(dy, f_sub(a[5], a[7])));
+        const PairStrict o = boundary ? force_pair_strict<false, false, false>(k, dx, dy, d2, xu, a[9], a[11], a[8], a[10], k.mass)
+                                      : force_pair_strict<true, false, false>(k, dx, dy, d2, xu, a[9], a[11], a[8], a[10], k.mass);
+        out[2 * i] = o.tx;
+        out[2 * i + 1] = o.ty;
     }
 }
 

@@ -5,14 +5,17 @@ Tolerances — written here, justified in DESIGN.md "Parity":
   rho, p, psi  vs the chain oracle (deterministic mode)          bit-for-bit
   rho          vs the libm-powf oracle / reference golden        1e-6 relative  (north star 1e-4)
   p            vs the libm-powf oracle / reference golden        max(1e-4*p, 160 Pa)
-  a            vs the chain oracle, same rho/p                   ||da|| <= 1e-4*max(||a||, G)
-  a            vs reference golden through the operator API      same bound (inputs identical)
+  a, u, v      vs the chain oracle (default mode)                 bit-for-bit: k_force evaluates :317-337,
+                                                                  :52-62, :219-228 in the reference's own types
+                                                                  and order, so whole runs are bit-identical
+  a            fast_force = 1 vs the chain oracle                 ||da|| <= 1e-4*max(||a||, G) (small scenes only)
+  a            vs reference golden through the operator API      ||da|| <= 1e-4*max(||a||, G) (libm powf there)
   non-deterministic mode                                         sets exact, rho 1e-6, a 1e-4 + p-noise
 """
 import numpy as np
 import pytest
 
-from conftest import G, same_bits
+from conftest import G, same_bits, same_bits_nan
 
 pytestmark = pytest.mark.gpu
 
@@ -24,6 +27,10 @@ FIELDS = ("x", "y", "u", "v", "m", "rho", "p")
 def accel_err(du, dv, rdu, rdv):
     d = np.hypot(du.astype("f8") - rdu, dv.astype("f8") - rdv)
     return d / np.maximum(np.hypot(rdu.astype("f8"), rdv), 9.81)
+
+
+def same_accel(du, dv, odu, odv):
+    return same_bits_nan(du, odu) and same_bits_nan(dv, odv)
 
 
 def p_ok(p, pref):
@@ -72,8 +79,14 @@ def test_one_pass_parity_resident_tier(request, oracle_built, lib_built, name, R
     assert same_bits(b["m"], ob["m"])
     assert same_bits(f["rho"], of["rho"])
     assert same_bits(f["p"], of["p"])
-    # acceleration
-    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    # acceleration: bit-for-bit; fast_force = 1 within the tolerance
+    assert same_accel(du, dv, odu, odv)
+    fsim = run_gpu(lib_built, R, fluid, binit, fast_force=True)
+    fsim.compute_accel(*G)
+    ff, fdu, fdv = fsim.download()
+    fsim.close()
+    assert same_bits(ff["rho"], of["rho"]) and same_bits(ff["p"], of["p"])
+    assert accel_err(fdu, fdv, odu, odv).max() < TOL_A and not same_accel(fdu, fdv, odu, odv)
     # against the reference-built golden (libm powf)
     ref = g[f"fluid_{snap}"]
     assert (np.abs(b["m"] - g["boundary"]["m"]) / g["boundary"]["m"]).max() < TOL_RHO
@@ -152,8 +165,10 @@ def test_render_matches_reference_frame(lib_built, golden075):
 
 
 def test_multi_step_against_oracle(oracle_built, lib_built, golden075):
-    """100 free-fall steps (p == 0): positions bit-for-bit; then through the impact, the
-    integral quantities the north star names."""
+    """100 free-fall steps (p == 0): every field bit-for-bit with the chain oracle, and close to the
+    reference-built golden (libm powf: its last-bit differences in powf(x, 3|4) feed the velocities);
+    then through the impact: still bit-for-bit with the chain oracle at step 2000, and against the golden
+    the integral quantities the north star names."""
     g = golden075
     sim = run_gpu(lib_built, 0.075, g["fluid_init"], g["boundary_init"])
     sim.compute_accel(*G)
@@ -161,12 +176,21 @@ def test_multi_step_against_oracle(oracle_built, lib_built, golden075):
     f, du, dv = sim.download()
     r = g["fluid_100"]
     assert np.abs(f["x"] - r["x"]).max() < 1e-6 and np.abs(f["y"] - r["y"]).max() < 1e-6
-    assert max(np.abs(f["u"] - r["u"]).max(), np.abs(f["v"] - r["v"]).max()) < 2e-6
+    assert max(np.abs(f["u"] - r["u"]).max(), np.abs(f["v"] - r["v"]).max()) < 5e-6
     assert (np.abs(f["rho"] - r["rho"]) / r["rho"]).max() < TOL_RHO
+    o, of, ob, gf, gb, odu, odv = oracle_state(oracle_built, 0.075, "chain", g["fluid_init"], g["boundary_init"])
+    o.step(of, ob, gf, gb, odu, odv, 100, *G)
+    for fld in FIELDS:
+        assert same_bits(f[fld], of[fld]), fld
+    assert same_accel(du, dv, odu, odv)
     # continue to step 2000 (impact at ~1600): chaotic divergence allowed per particle, the
     # integrals must stay close to the reference's
     sim.step(1900, *G)
     f, du, dv = sim.download()
+    o.step(of, ob, gf, gb, odu, odv, 1900, *G)
+    for fld in FIELDS:
+        assert same_bits(f[fld], of[fld]), fld               # 2000 steps, through the impact
+    assert same_accel(du, dv, odu, odv)
     r = g["fluid_2000"]
     st = sim.stats()
     m = r["m"].astype("f8")
@@ -208,8 +232,8 @@ def test_one_step_from_post_impact_state(oracle_built, lib_built, golden02):
     for fld in ("x", "y"):
         assert same_bits(f[fld], of[fld]), fld             # kick1 + drift are exact
     assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])
-    assert accel_err(du, dv, odu, odv).max() < TOL_A
-    assert max(np.abs(f["u"] - of["u"]).max(), np.abs(f["v"] - of["v"]).max()) < 1e-4 * 0.5 * float(o.dt) * 4e3 + 1e-6
+    assert same_accel(du, dv, odu, odv)
+    assert same_bits(f["u"], of["u"]) and same_bits(f["v"], of["v"])
     assert np.array_equal(sim.cell_ids(), o.cell_ids(gf, of))
     sim.close()
 
@@ -242,7 +266,7 @@ def test_per_particle_mass_path(oracle_built, lib_built, golden02):
     o, of, ob, gf, gb, odu, odv = oracle_state(oracle_built, 0.02, "chain", fluid, g["boundary_init"])
     assert same_bits(f["m"], fluid["m"])
     assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])
-    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    assert same_accel(du, dv, odu, odv)
     sim.close()
 
 
@@ -256,8 +280,9 @@ def test_time_varying_gravity_trace(oracle_built, lib_built, golden075):
     f, du, dv = sim.download()
     o, of, ob, gf, gb, odu, odv = oracle_state(oracle_built, 0.075, "chain", g["fluid_init"], g["boundary_init"])
     o.step(of, ob, gf, gb, odu, odv, 60, gxy=trace)
-    assert np.abs(f["x"] - of["x"]).max() < 1e-6 and np.abs(f["u"] - of["u"]).max() < 5e-6
-    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    for fld in FIELDS:
+        assert same_bits(f[fld], of[fld]), fld            # 60 whole steps, every field
+    assert same_accel(du, dv, odu, odv)
     sim.close()
 
 
@@ -277,7 +302,7 @@ def test_edge_no_boundary_single_particle_and_ragged_sizes(oracle_built, lib_bui
         empty = np.zeros(0, oracle_built.PARTICLE); gb = o.grid(0); o.grid_update(gb, empty)
         odu, odv = o.compute_accel(of, empty, gf, gb, *G)
         assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"]), n
-        assert accel_err(du, dv, odu, odv).max() < TOL_A, n
+        assert same_accel(du, dv, odu, odv), n
         sim.close()
 
 
@@ -303,7 +328,7 @@ def test_edge_crowded_cell_flushes_the_neighbour_list(oracle_built, lib_built):
     odu, odv = o.compute_accel(of, empty, gf, gb, *G)
     assert o.ctr.neighbor_overflows == 0 and o.ctr.max_neighbors_seen == counts.max()
     assert same_bits(f["rho"], of["rho"])
-    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    assert same_accel(du, dv, odu, odv)
     sim.close()
 
 
@@ -326,8 +351,7 @@ def test_edge_sparse_scene_uses_unstaged_tiles(oracle_built, lib_built):
     o2, of, ob, gf, gb, odu, odv = oracle_state(oracle_built, R, "chain", fluid, boundary)
     assert np.array_equal(sim.cell_ids(), o2.cell_ids(gf, of))
     assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])
-    ok = ~np.isnan(odu)
-    assert accel_err(du[ok], dv[ok], odu[ok], odv[ok]).max() < TOL_A
+    assert same_accel(du, dv, odu, odv)
     sim.close()
 
 
@@ -474,7 +498,7 @@ def test_full_size_config2_properties(oracle_built, lib_built):
     assert np.array_equal(sim.cell_ids(), o.cell_ids(gf, of))
     assert same_bits(sim.download_boundary()["m"], ob["m"])
     assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])
-    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    assert same_accel(du, dv, odu, odv)
     cand, acc = sim.pair_stats()
     assert 50 < cand < 70 and 17 < acc < 23          # C ~ 60, P ~ 20 on the rest lattice
     # 50 steps: permutation intact, mass exact, momentum = m*g*t to round-off, KE consistent
@@ -488,12 +512,11 @@ def test_full_size_config2_properties(oracle_built, lib_built):
     assert st["mom_y"] == pytest.approx(-9.81 * t * m.sum(), rel=2e-3)
     assert abs(st["mom_x"]) < 1e-4 * abs(st["mom_y"])
     assert st["n_escaped"] == 0 and st["max_cell_count"] < 20
-    # oracle after the same 50 steps (free fall, p == 0): positions agree to round-off
+    # oracle after the same 50 steps: every field bit-for-bit
     o.step(of, ob, gf, gb, odu, odv, 50, *G)
-    assert np.abs(f2["x"] - of["x"]).max() < 1e-6 and np.abs(f2["y"] - of["y"]).max() < 1e-6
-    # after 50 steps positions differ by <= 2 ulp (2.4e-7 m at x ~ 2-4 m) = 1.5e-4 H at this
-    # spacing, which moves rho by ~4e-6: the north-star tolerance, not the one-pass one, applies
-    assert (np.abs(f2["rho"].astype("f8") - of["rho"]) / of["rho"]).max() < 1e-4
+    for fld in FIELDS:
+        assert same_bits(f2[fld], of[fld]), fld
+    assert same_accel(du2, dv2, odu, odv)
     # run-to-run reproducibility of the deterministic mode
     sim2 = lib_built.Simulation(prm)
     sim2.upload(fluid, boundary); sim2.init_boundary(); sim2.compute_accel(*G); sim2.step(50, *G)
@@ -519,25 +542,18 @@ def test_full_size_config3_dam_break_4m(oracle_built, lib_built):
     assert np.array_equal(sim.cell_ids(), o.cell_ids(gf, of))                         # exact
     assert same_bits(sim.download_boundary()["m"], ob["m"])                          # psi bit-for-bit
     assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])             # bit-for-bit
-    # Acceleration: an interior particle's a = g - (a cancelling sum of ~20 artificial-pressure pair
-    # terms, :325), and the term size grows like 1/H: at this spacing the uncancelled half-sum at the
-    # free surface is max|a| ~ 1100 m/s^2 while the result is ~ G.  Rounding noise scales with the
-    # terms, not with the result, so the floor of the relative error is max(G, 0.1 max|a|) here
-    # (measured: 3.5e-3 m/s^2 absolute = 3.2e-6 of max|a|; 3.6e-4 of G).  At R >= 0.0024 the terms are
-    # <= 230 m/s^2 and the plain floor G of the other tests holds.
-    a_ref = np.hypot(odu.astype("f8"), odv)
-    floor = max(9.81, 0.1 * a_ref.max())
-    err = np.hypot(du.astype("f8") - odu, dv.astype("f8") - odv) / np.maximum(a_ref, floor)
-    assert err.max() < TOL_A
-    assert np.median(accel_err(du, dv, odu, odv)) < 2e-5      # with the plain floor G: measured 5.3e-6
+    # Acceleration: bit-for-bit.  (An interior particle's a = g - (a cancelling sum of ~20 artificial-
+    # pressure pair terms, :325) whose size grows like 1/H — max|a| ~ 1100 m/s^2 at the free surface
+    # here — so only the reference's own roundings meet the 1e-4*max(|a|, G) bar at this size: the
+    # fast_force arithmetic measures 3.6e-4 of G.)
+    assert same_accel(du, dv, odu, odv)
     sim.step(5, *G)
     o.step(of, ob, gf, gb, odu, odv, 5, *G)
     f5, du5, dv5 = sim.download()
     st = sim.stats()
-    assert np.abs(f5["x"] - of["x"]).max() < 1e-6 and np.abs(f5["y"] - of["y"]).max() < 1e-6
-    # positions may differ by an ulp after five steps, which moves rho by ~1e-6 (and p by 7x that
-    # times B): the north-star tolerance, not the one-pass one, applies from here on
-    assert (np.abs(f5["rho"].astype("f8") - of["rho"]) / of["rho"]).max() < 1e-4
+    for fld in FIELDS:
+        assert same_bits(f5[fld], of[fld]), fld                                       # five whole steps
+    assert same_accel(du5, dv5, odu, odv)
     assert same_bits(f5["m"], fluid["m"])                                            # permutation intact
     assert st["mass"] == pytest.approx(fluid["m"].astype("f8").sum(), rel=1e-12)
     assert st["n_escaped"] == 0 and st["n_fluid"] == len(fluid)
@@ -566,9 +582,13 @@ def test_dam_break_scene_steps(oracle_built, lib_built):
     o, of, ob, gf, gb, odu, odv = oracle_state(oracle_built, R, "chain", fluid, boundary)
     f, du, dv = sim.download()
     assert same_bits(f["rho"], of["rho"]) and same_bits(f["p"], of["p"])
-    assert accel_err(du, dv, odu, odv).max() < TOL_A
+    assert same_accel(du, dv, odu, odv)
     sim.step(200, *G)
     o.step(of, ob, gf, gb, odu, odv, 200, *G)
+    f2, du2, dv2 = sim.download()
+    for fld in FIELDS:
+        assert same_bits(f2[fld], of[fld]), fld            # 200 whole steps, every field
+    assert same_accel(du2, dv2, odu, odv)
     st = sim.stats()
     m = of["m"].astype("f8")
     ke = 0.5 * (m * (of["u"].astype("f8") ** 2 + of["v"].astype("f8") ** 2)).sum()
