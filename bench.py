@@ -6,8 +6,12 @@
 One "step" = one leapfrog step (kick, drift, cell build, density+pressure, accelerations,
 kick: pi_sph_fluid.c:612-641) over every fluid particle of the workload.
 
-N = 1 workload: BASELINE.json configs[1] — the reference's drop scene scaled to R = 0.002423
-(262,204 fluid + 4,954 boundary particles), synthetic (the reference's own lattice).
+Workload at EVERY N (strong scaling, so the 1 -> 8 GPU curve is one configuration): BASELINE.json
+configs[3], the 64M-particle 2-D dam break — on one GPU at N = 1 (it fits: ~170 B x 64M of 180 GB),
+as x-slabs with halo exchange over NVLink at N = 2, 4, 8.  The N = 1 line also carries, as named
+`secondary` entries measured in the same run, configs[1] (the reference's drop scene at 262,204
+particles, with the reference's own compiled code as its CPU arm) and configs[2] (4M dam break), and
+the cost of the reference-arithmetic force pass against fast_force.
 
 Keys of the JSON line (see the round prompt for the contract):
   value         whole-job fluid-particle-updates/s, state resident in HBM, CUDA events on the
@@ -235,14 +239,16 @@ def run_reference(spec, steps: int, warmup: int, budget_s: float = 90.0):
             t0 = time.perf_counter(); o.step(fluid, boundary, gf, gb, du, dv, n, *G); return time.perf_counter() - t0
     t_probe = run(max(1, min(warmup, 3)))
     per_step = t_probe / max(1, min(warmup, 3))
-    n_run = int(max(1, min(steps, budget_s / max(per_step, 1e-9))))
+    # at least ~2.5 s of timed steps whatever K is (a 0.2 s sample is noise), at most the budget
+    n_run = int(max(1, min(max(steps, 2.5 / max(per_step, 1e-9)), budget_s / max(per_step, 1e-9))))
     t = run(n_run)
     return {"value": len(fluid) * n_run / t, "unit": UNIT, "cores": int(cores), "kind": kind,
-            "sample": f"{n_run} of {steps} steps of the full {len(fluid)}-particle scene, {t:.2f} s",
+            "sample": f"{n_run} steps (asked: {steps}; at least 2.5 s are timed) of the full {len(fluid)}-particle scene, {t:.2f} s",
             "ms_per_step": 1e3 * t / n_run, "n_fluid": int(len(fluid)), "steps_run": n_run}
 
 
-def run_reference_block(spec, steps: int, warmup: int, budget_s: float, sample_particles: float = 1.0e6):
+def run_reference_block(spec, steps: int, warmup: int, budget_s: float, sample_particles: float = 1.0e6,
+                        min_timed_s: float = 3.0):
     """Dam-break scenes are not in the reference (its main() hard-codes the drop and R is a macro),
     so the CPU arm for them is the oracle port (same operators, the reference's shipped -Ofast flags,
     OpenMP on all host cores) on a BOUNDED SAMPLE: the leftmost part of the same block at the same
@@ -252,6 +258,9 @@ def run_reference_block(spec, steps: int, warmup: int, budget_s: float, sample_p
     o = pyoracle.Oracle(R=R, variant="fast", threads=host_cores())
     x1, y1 = spec["block"] if "block" in spec else (spec["box"][1], spec["box"][3])
     ny = max(1.0, (y1 - 2 * R) / R)
+    # the timed region should last a few seconds whatever K is: a sub-block of ~1M particles takes ~30 ms per
+    # step on 16-32 host threads, so grow the sample when K is small (bounded by 8M particles and the block)
+    sample_particles = min(8.0e6, max(sample_particles, min_timed_s * 3.0e7 / max(1, steps)))
     width = min(x1 - 2 * R, max(8 * 2.6 * R, sample_particles / ny * R))
     fluid = o.scene_block(2 * R, 2 * R + width, 2 * R, y1)
     boundary = o.scene_boundary()
@@ -271,16 +280,21 @@ def run_reference_block(spec, steps: int, warmup: int, budget_s: float, sample_p
 
 # ------------------------------------------------------------------------------------------ GPU arm
 
-def run_gpu(args, spec, rank, world):
+def run_gpu(args, spec, rank, world, K=None, W=None, want_e2e=True, fast_force=None, workload_key=None):
+    """One GPU, any scene.  K / W / fast_force default to the command line's; the secondary entries of the
+    N = 1 line call this again with their own."""
     import torch
     import pi_sph_fluid_b200 as pkg
 
     dev = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(dev)
+    fast_force = args.fast_force if fast_force is None else fast_force
     prm, fluid, boundary = build_scene(pkg, spec, deterministic=not args.nondeterministic, device=dev,
-                                       fast_force=args.fast_force)
+                                       fast_force=fast_force)
     n = len(fluid)
-    K, W = args.steps, max(args.warmup, 3)
+    K = args.steps if K is None else K
+    W = max(args.warmup if W is None else W, 3)
+    workload_key = workload_key or args.workload
 
     sim = pkg.Simulation(prm)
     stream = torch.cuda.ExternalStream(sim.stream, device=dev)
@@ -297,7 +311,7 @@ def run_gpu(args, spec, rank, world):
     clocks.wait_first()
     t_w = time.perf_counter()
     while time.perf_counter() - t_w < 0.4:
-        sim.step(50, *G)
+        sim.step(50 if n < 4_000_000 else 5, *G)
         sim.synchronize()
     cand, acc = sim.pair_stats()
 
@@ -356,11 +370,13 @@ def run_gpu(args, spec, rank, world):
     force_ms = prof["force"]["ms"] / max(1, prof["force"]["launches"])
     dens_ms = prof["density"]["ms"] / max(1, prof["density"]["launches"])
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    roofline = make_roofline(args.workload, n, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_max_mhz, peak_src, sm_count)
+    roofline = make_roofline(workload_key, n, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_max_mhz, peak_src, sm_count)
 
-    if args.no_e2e:
+    if args.no_e2e or not want_e2e:
         sim.close()
-        return {"metric": METRIC, "value": value, "ms_per_step": gpu_ms / K, "roofline": roofline, "tuning_run": True}
+        return {"metric": METRIC, "value": value, "ms_per_step": gpu_ms / K, "roofline": roofline, "tuning_run": True,
+                "steps": K, "n_fluid": n, "warm_l2_value": total_particles * K / (warm_ms * 1e-3), "clocks": clk,
+                "gpu_launches": int(launches), "fast_force": bool(fast_force)}
     # ---- e2e: host buffers -> C ABI -> host buffers, copies inside the timed region
     fl_pin = torch.empty(n * 7, dtype=torch.float32).pin_memory()
     bd_pin = torch.empty(len(boundary) * 7, dtype=torch.float32).pin_memory()
@@ -415,11 +431,17 @@ def run_gpu(args, spec, rank, world):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic (the reference's own lattice drop scene, pi_sph_fluid.c:484-540)",
+        "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (f64 at the reference's double sites: pi_sph_fluid.c:325, :332, :334, :616)",
+        "data": ("synthetic (the reference's own lattice drop scene, pi_sph_fluid.c:484-540)" if spec["scene"] == "drop" else
+                 "synthetic (dam-break block on the reference's lattice idiom; not a reference scene)"),
         "config": {"workload": spec["name"], "n_fluid": n, "n_boundary": int(len(boundary)), "R": spec["R"],
                    "deterministic_order": not args.nondeterministic,
-                   "l2": "flushed between timed steps (256 MiB write on the same stream, untimed)",
+                   "force_arithmetic": ("fast_force = 1: single precision, approximate rsqrt/rcp (outside the 1e-4 parity bar at >= 4M particles)"
+                                        if fast_force else
+                                        "the reference's own (default): du_dt, dv_dt and whole runs bit-identical with the oracle"),
+                   "l2": "flushed between timed steps (256 MiB write on the same stream, untimed)"
+                         + ("; the state (~170 B/particle) is also far larger than the 126 MB L2" if n > 2_000_000 else ""),
                    "warm_l2_value": total_particles * K / (warm_ms * 1e-3),
                    "timing": "CUDA events on the library stream around each step; max over ranks",
                    "wall_s_timed_region": round(t_wall, 4),
@@ -432,23 +454,15 @@ def run_gpu(args, spec, rank, world):
 
 
 def scaling_note():
-    """The N = 1 line runs BASELINE configs[1] (262k particles), the N > 1 lines 8M particles per GPU:
-    the number to hold an N-GPU line against is the same 8M-particle load on ONE GPU, measured with
-    `bench.py --workload dam8m` and committed under profiles/."""
-    note = {"per_gpu_load_at_n_gt_1": "dam break, 8M particles per GPU (N = 8: BASELINE configs[3], 64M)",
-            "n1_workload": "BASELINE configs[1], 262,204 particles (latency-bound: 6 kernels of ~10 us)"}
-    try:
-        files = sorted((ROOT / "profiles").glob("r*_bench_dam8m*.json"))
-        j = json.loads(files[-1].read_text().strip().splitlines()[-1])
-        note["one_gpu_on_8m_particles"] = {"value": j["value"], "ms_per_step": j["ms_per_step"], "source": f"profiles/{files[-1].name}"}
-    except Exception:
-        pass
-    return note
+    """Every N runs the SAME configuration (BASELINE configs[3], the 64M-particle dam break): strong scaling,
+    so value(N) / (N x value(1)) is the parallel efficiency.  `--workload` overrides it (tuning, other configs)."""
+    return {"family": "strong scaling on BASELINE configs[3]: one 64M-particle dam break at every N",
+            "n1": "the whole 64M-particle scene on one B200", "n_gt_1": "x-slabs of it, 64M / N particles per GPU"}
 
 
 def run_gpu_slabs(args, spec, rank, world):
     """N > 1: the dam-break block cut into x-slabs at the particle-count quantiles, one process per GPU,
-    halo + migration over NCCL (sphb_mg_*).  Weak scaling: the workload has 8M particles per GPU."""
+    halo + migration as peer stores over NVLink (or NCCL send/recv).  Strong scaling: the same scene at every N."""
     import torch
     import torch.distributed as dist
     import pi_sph_fluid_b200 as pkg
@@ -602,7 +616,7 @@ def run_gpu_slabs(args, spec, rank, world):
     dens_ms = prof["density"]["ms"] / max(1, prof["density"]["launches"])
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     # per-GPU load is the 8M-particle dam-break slab: the committed ncu capture of dam8m is the matching one
-    roofline = make_roofline("dam8m", n_local, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_max_mhz, peak_src,
+    roofline = make_roofline(f"dam{max(1, round(n_total / world / 1e6))}m", n_local, kern, force_ms, dens_ms, cand, acc, hbm_peak, sm_max_mhz, peak_src,
                              sm_count, suffix=" (rank 0)")
     roofline["kernels_per_rank_ms"] = per_rank_ms
 
@@ -651,8 +665,9 @@ def run_gpu_slabs(args, spec, rank, world):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": ("synthetic (filled tank on the reference's lattice idiom, gravity from a synthetic MPU6050 tilt trace mapped as pi_sph_fluid.c:439-440; not a reference scene)"
+        "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (f64 at the reference's double sites: pi_sph_fluid.c:325, :332, :334, :616)",
+        "data": ("synthetic (filled tank on the reference's lattice idiom, gravity from a synthetic MPU6050 tilt trace mapped as pi_sph_fluid.c:439-440; not a reference scene)"
                                  if tilt else "synthetic (dam-break block on the reference's lattice idiom; not a reference scene)"),
         "config": {"workload": spec["name"], "n_fluid": n_total, "n_boundary": int(len(boundary)), "R": R,
                    "particles_per_gpu": [int(hist[int(cuts[r]):int(cuts[r + 1])].sum()) for r in range(world)],
@@ -663,6 +678,8 @@ def run_gpu_slabs(args, spec, rank, world):
                    "transport": transport, **({"transport_fallback": transport_note[0][:200]} if transport_note else {}),
                    "halo_message_bytes": info["message_bytes"], "particle_slots_per_gpu": info["particle_capacity"],
                    "deterministic_order": not args.nondeterministic,
+                   "force_arithmetic": ("fast_force = 1" if args.fast_force else
+                                        "the reference's own (default): bit-identical with the oracle and with the 1-GPU run"),
                    "gravity": (f"tilt trace: +-{tilt[0]} deg, period {tilt[1]} steps, sample held {tilt[2]} steps, one (gx, gy) per step" if tilt else "constant (0, -9.81)"),
                    "l2": f"not flushed: per-GPU state (~100 B x {n_total / world / 1e6:.0f}M particles) is far larger than the 126 MB L2",
                    "timing": "CUDA events on the library stream around the K steps, barrier + synchronize both sides; max over ranks",
@@ -686,6 +703,7 @@ def main():
     ap.add_argument("--nondeterministic", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg")
+    ap.add_argument("--no-secondary", action="store_true", help="N = 1: skip the secondary entries (configs[1], configs[2], fast_force)")
     ap.add_argument("--fast-force", action="store_true",
                     help="sphb_params.fast_force = 1: the single-precision force arithmetic (outside the 1e-4 parity bar "
                          "at >= 4M particles) instead of the reference's own (default, bit-identical accelerations)")
@@ -694,11 +712,11 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.steps is None:
-        args.steps = 500 if world == 1 else 200
+        args.steps = 100 if world == 1 else 200
     if args.warmup is None:
-        args.warmup = 20 if world == 1 else 10
-    # N = 1: BASELINE configs[1].  N > 1: dam break with 8M particles per GPU (N = 8 is configs[3], 64M)
-    args.workload = args.workload or ("drop256k" if world == 1 else f"dam{8 * world}m")
+        args.warmup = 5 if world == 1 else 10
+    # every N: BASELINE configs[3], the 64M-particle dam break (strong scaling)
+    args.workload = args.workload or "dam64m"
     spec = workload_spec(args.workload)
 
     if args.impl == "reference":
@@ -710,11 +728,15 @@ def main():
             return 0
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": ("synthetic (the reference's own lattice drop scene)" if spec["scene"] == "drop" else
                          "synthetic (dam-break block on the reference's lattice idiom; bounded sub-block sample)"),
                 "config": {"workload": spec["name"], "n_fluid": r["n_fluid"], "R": spec["R"],
-                           "threads": r["cores"], "flags": "-Ofast -march=x86-64-v3|v4 -fopenmp (Makefile:2,4; -march pinned for portability)"},
+                           "threads": r["cores"], "flags": "-Ofast -march=x86-64-v3|v4 -fopenmp (Makefile:2,4; -march pinned for portability)",
+                           "same_config_note": ("the reference's main() hard-codes the drop scene and R (pi_sph_fluid.c:11, :484-506), so a dam break "
+                                                "runs through the oracle port of its operators (same shipped flags) on a sub-block of the same block at "
+                                                "the same spacing; particle-updates/s is a per-particle rate, so the sample size does not enter the ratio"
+                                                if r["kind"] == "port" else "the reference's own compiled translation unit on the whole scene")},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -729,6 +751,8 @@ def main():
     if world == 1 and "tilt" in spec:
         raise SystemExit("bench.py: the sloshing workload is a slab (multi-GPU) bench line: launch it under torchrun with --gpus 2|4|8")
     line = run_gpu_slabs(args, spec, rank, world) if world > 1 else run_gpu(args, spec, rank, world)
+    if rank == 0 and world == 1 and not args.no_e2e and not args.no_secondary:
+        line["secondary"] = secondary_entries(args, spec, line)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             r = run_reference(spec, 2000, 3, budget_s=15.0)
@@ -737,6 +761,38 @@ def main():
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
+
+
+def secondary_entries(args, spec, main_line):
+    """Named secondary measurements of the N = 1 line, taken in the same process right after the main workload:
+    BASELINE configs[1] and configs[2] (unless one of them IS the main workload), and the main workload's force
+    pass in fast_force arithmetic — the cost of the reference-arithmetic force pass the headline is measured with."""
+    out = {}
+    for key, K2 in (("drop256k", 300), ("dam4m", 100)):
+        if key == args.workload:
+            continue
+        sp = workload_spec(key)
+        l2 = run_gpu(args, sp, 0, 1, K=K2, W=10, want_e2e=(key == "drop256k"), workload_key=key)
+        ent = {"workload": sp["name"], "value": l2["value"], "unit": UNIT, "ms_per_step": l2["ms_per_step"], "steps": K2,
+               "n_fluid": l2.get("n_fluid", l2.get("config", {}).get("n_fluid")),
+               "kernels_ms": {k_: v["ms"] for k_, v in l2["roofline"]["kernels"].items()}}
+        if "e2e" in l2:
+            ent["e2e"] = l2["e2e"]
+        if key == "drop256k" and not args.no_cpu_baseline:
+            r = run_reference(sp, 2000, 3, budget_s=10.0)
+            if r:
+                ent["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+        out[key] = ent
+    if not args.fast_force:
+        K3 = max(3, min(args.steps, 30))
+        lf = run_gpu(args, spec, 0, 1, K=K3, W=3, want_e2e=False, fast_force=True)
+        km, kf = main_line["roofline"]["kernels"], lf["roofline"]["kernels"]
+        out["fast_force_on_main_workload"] = {
+            "workload": spec["name"], "value": lf["value"], "ms_per_step": lf["ms_per_step"], "steps": K3,
+            "force_ms": {"reference_arithmetic": km["force"]["ms"], "fast_force": kf["force"]["ms"]},
+            "note": "fast_force = 1 is NOT the headline: its accelerations are outside 1e-4*max(|a|, G) at >= 4M particles "
+                    "(tests/test_gpu_parity.py); the headline value is measured with the reference's arithmetic"}
+    return out
 
 
 if __name__ == "__main__":

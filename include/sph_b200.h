@@ -90,7 +90,10 @@ typedef struct sphb_stats {
     unsigned long long steps;
     unsigned int n_lost;            /* slabs: particles that moved > 2 cell columns in one step  */
     unsigned int n_overflow;        /* slabs: halo message or slot capacity exceeded (fatal);    */
-                                    /*   bit 30: a neighbour's message did not arrive in 20 s    */
+                                    /*   bit 30: a neighbour's message did not arrive in 20 s —  */
+                                    /*   sphb_synchronize, sphb_get_stats, sphb_step_stats[_end] */
+                                    /*   and sphb_mg_download then return SPHB_E_COMM            */
+    /* n_escaped and max_cell_count describe the LAST grid build of the fluid (not a running total).   */
 } sphb_stats;
 
 typedef struct sphb_ctx sphb_ctx;
@@ -177,6 +180,14 @@ int sphb_grid_shape(sphb_ctx *ctx, int *n_cells_rows, int *m_cells_cols);
  * indices in this library's visiting order (== the reference's order when
  * deterministic = 1).  Returns the number of particles whose count exceeded cap. */
 int sphb_neighbor_lists(sphb_ctx *ctx, int which, int cap, int *counts, int *lists);
+
+/* The fluid-fluid neighbour lists of the hot path itself: what the density pass of the last
+ * sphb_compute_accel / sphb_step found (find_neighbors, :126-153) and handed to the force pass, decoded from
+ * the device representation (tile offsets per chunk of 128 sorted particles + the chunk's staging plan) back
+ * to ORIGINAL indices in visiting order.  counts[i] = -1 where no list was handed over for particle i (the
+ * force pass searches again for it: list flushed or its part of the chunk not staged).  *n_whole_chunks =
+ * chunks whose plan travelled in the chunk record.  Single-GPU contexts. */
+int sphb_handover_lists(sphb_ctx *ctx, int cap, int *counts, int *lists, unsigned int *n_whole_chunks);
 
 /* The pair term m_j*temp_ij*grad_a W_ij of calculate_accelerations (:317-337, :52-62, :226) for n
  * caller-given pairs, one device thread per pair — the device instruction sequences of the force pass

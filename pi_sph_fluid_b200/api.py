@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
         "sphb_profile_read": (ci, [vp, vp, vp, ci]),
         "sphb_pair_stats": (ci, [vp, vp, vp]),
         "sphb_probe_force_pair": (ci, [vp, ci, vp, ci, vp, vp]),
+        "sphb_handover_lists": (ci, [vp, ci, vp, vp, vp]),
         "sphb_flush_l2": (ci, [vp]),
         "sphb_stream": (vp, [vp]),
         "sphb_launch_count": (C.c_ulonglong, [vp]),
@@ -357,6 +358,14 @@ class Simulation:
         lists = np.zeros((n, cap), np.int32)
         over = _check(lib().sphb_neighbor_lists(self._h, which, cap, _p(counts), _p(lists)), "sphb_neighbor_lists")
         return counts, lists, over
+
+    def handover_lists(self, cap: int = 64):
+        """sphb_handover_lists -> (counts, lists, chunks whose plan travelled in the record)."""
+        counts = np.zeros(self.n_fluid, np.int32)
+        lists = np.zeros((self.n_fluid, cap), np.int32)
+        whole = C.c_uint(0)
+        _check(lib().sphb_handover_lists(self._h, cap, _p(counts), _p(lists), C.byref(whole)), "sphb_handover_lists")
+        return counts, lists, int(whole.value)
 
     def probe_force_pair(self, pairs: np.ndarray, variant: int = 0):
         """sphb_probe_force_pair: (n, 12) float32 pairs -> ((n, 2) float32 pair terms, shortcuts verified?)."""

@@ -78,7 +78,7 @@ k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *
             pos[s] = p;
         }
         cell_of_window(k, p.x, p.y, row, col, clamped, outside);          // :111-112
-        if (clamped) atomicAdd(&ctr->n_escaped, 1u);
+        if (clamped) atomicAdd(&ctr->escaped_acc, 1u);
         if (outside) {
             key[s] = kTrashKey;
         } else {
@@ -356,7 +356,7 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
             uint32_t m = 0;
 #pragma unroll
             for (int w = 0; w < kScanThreads / 32; w++) m = s_warp_max[w] > m ? s_warp_max[w] : m;
-            if (m) atomicMax(&ctr->max_cell_count, m);
+            if (m) atomicMax(&ctr->max_cell_acc, m);
             if ((int)tile == n_tiles - 1) {
                 start[n] = excl + aggregate;
                 if (n_out) *n_out = (int)(excl + aggregate);     // slabs: particles the sort keeps
@@ -479,6 +479,7 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
     if (has_mass) ps.mc ^= 1;
     if (has_aux) ps.xc ^= 1;
     ps.sorted = true;
+    ps.counters_dirty = true;
     ps.lists_valid = false;          // the handed-over neighbour lists describe the previous order
     return launches;
 }

@@ -153,8 +153,10 @@ struct ProfScope {
 int build_grid(sphb_ctx *c, ParticleSet &ps, bool advect, const Consts *kk, const StepStats *deliver)
 {
     const Consts &k = kk ? *kk : c->k;
-    { ProfScope p(c, SPHB_K_ADVECT_BIN); c->launches += launch_advect_bin(c->stream, k, ps, advect, c->d_counters, nullptr, deliver); }
-    { ProfScope p(c, SPHB_K_SCAN); c->launches += launch_scan(c->stream, k, ps, c->scan, c->d_counters); }
+    // the boundary's builds count into their own block, so the fluid's per-build counters stay the fluid's
+    DeviceCounters *ctr = (&ps == &c->boundary) ? c->d_counters + 1 : c->d_counters;
+    { ProfScope p(c, SPHB_K_ADVECT_BIN); c->launches += launch_advect_bin(c->stream, k, ps, advect, ctr, nullptr, deliver); }
+    { ProfScope p(c, SPHB_K_SCAN); c->launches += launch_scan(c->stream, k, ps, c->scan, ctr); }
     { ProfScope p(c, SPHB_K_REORDER); c->launches += launch_reorder(c->stream, k, ps, c->prm.deterministic != 0); }
     return SPHB_OK;
 }
@@ -216,7 +218,8 @@ static int check_device(int device)
     if (device < 0 || device >= count) { set_error("device %d out of range (%d devices)", device, count); return SPHB_E_ARG; }
     cudaDeviceProp prop;
     SPHB_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
+    if (prop.major != 10 || prop.minor != 0) {
+        // sm_100a code is not forward compatible: an sm_103 part has no loadable image of these kernels
         set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         return SPHB_E_CUDA;
     }
@@ -274,6 +277,36 @@ int sphb_gravity_from_raw(const sphb_params *prm, int accel_x_raw, int accel_y_r
     return SPHB_OK;
 }
 
+static int create_fill(sphb_ctx *c, const sphb_params *prm)
+{
+    c->prm = *prm;
+    c->device = prm->device;
+    c->k = make_consts(*prm, prm->rho0 * prm->vol);
+    cudaDeviceProp prop;
+    SPHB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    c->sm_count = prop.multiProcessorCount;
+    SPHB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_counters), 2 * sizeof(DeviceCounters)));
+    SPHB_CUDA(cudaMemset(c->d_counters, 0, 2 * sizeof(DeviceCounters)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_gravity), sizeof(float2) * 4096));
+    c->scan.n_tiles = (c->k.ncells + kScanTile - 1) / kScanTile;
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->scan.tile_state), sizeof(unsigned long long) * (c->scan.n_tiles + 1)));
+    SPHB_CUDA(cudaMemset(c->scan.tile_state, 0, sizeof(unsigned long long) * (c->scan.n_tiles + 1)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->scan.tile_counter), sizeof(unsigned long long)));
+    SPHB_CUDA(cudaMemset(c->scan.tile_counter, 0, sizeof(unsigned long long)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), 128));
+    SPHB_CUDA(cudaMemset(c->d_stats, 0, 128));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_step_slots), (size_t)2 * kStatsSlots * 128));      // two sets, by sequence parity
+    SPHB_CUDA(cudaMemset(c->d_step_slots, 0, (size_t)2 * kStatsSlots * 128));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats_done), sizeof(unsigned int)));
+    SPHB_CUDA(cudaMemset(c->d_stats_done, 0, sizeof(unsigned int)));
+    SPHB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c->h_stats), 512, cudaHostAllocMapped));     // two slots
+    memset(c->h_stats, 0, 512);
+    for (int i = 0; i < 128; i++) SPHB_CUDA(cudaEventCreate(&c->ev[i]));
+    SPHB_CUDA(cudaDeviceSynchronize());      // memsets above vs. the non-blocking stream
+    return SPHB_OK;
+}
+
 int sphb_create(const sphb_params *prm, sphb_ctx **out)
 {
     if (!prm || !out) { set_error("null argument"); return SPHB_E_ARG; }
@@ -292,31 +325,12 @@ int sphb_create(const sphb_params *prm, sphb_ctx **out)
 
     sphb_ctx *c = new (std::nothrow) sphb_ctx();
     if (!c) return SPHB_E_NOMEM;
-    c->prm = *prm;
-    c->device = prm->device;
-    c->k = make_consts(*prm, prm->rho0 * prm->vol);
-    cudaDeviceProp prop;
-    SPHB_CUDA(cudaGetDeviceProperties(&prop, c->device));
-    c->sm_count = prop.multiProcessorCount;
-    SPHB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_counters), sizeof(DeviceCounters)));
-    SPHB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)));
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_gravity), sizeof(float2) * 4096));
-    c->scan.n_tiles = (c->k.ncells + kScanTile - 1) / kScanTile;
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->scan.tile_state), sizeof(unsigned long long) * (c->scan.n_tiles + 1)));
-    SPHB_CUDA(cudaMemset(c->scan.tile_state, 0, sizeof(unsigned long long) * (c->scan.n_tiles + 1)));
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->scan.tile_counter), sizeof(unsigned long long)));
-    SPHB_CUDA(cudaMemset(c->scan.tile_counter, 0, sizeof(unsigned long long)));
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats), 128));
-    SPHB_CUDA(cudaMemset(c->d_stats, 0, 128));
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_step_slots), (size_t)2 * kStatsSlots * 128));      // two sets, by sequence parity
-    SPHB_CUDA(cudaMemset(c->d_step_slots, 0, (size_t)2 * kStatsSlots * 128));
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_stats_done), sizeof(unsigned int)));
-    SPHB_CUDA(cudaMemset(c->d_stats_done, 0, sizeof(unsigned int)));
-    SPHB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c->h_stats), 512, cudaHostAllocMapped));     // two slots
-    memset(c->h_stats, 0, 512);
-    for (int i = 0; i < 128; i++) SPHB_CUDA(cudaEventCreate(&c->ev[i]));
-    SPHB_CUDA(cudaDeviceSynchronize());      // memsets above vs. the non-blocking stream
+    for (int i = 0; i < 128; i++) c->ev[i] = nullptr;
+    rc = create_fill(c, prm);
+    if (rc) {                 // nothing leaks on a failed create: sphb_destroy tolerates the members still null
+        sphb_destroy(c);
+        return rc;
+    }
     *out = c;
     return SPHB_OK;
 }
@@ -325,7 +339,7 @@ int sphb_destroy(sphb_ctx *c)
 {
     if (!c) return SPHB_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     mg_free(c);
     free_set(c->fluid);
     free_set(c->boundary);
@@ -334,8 +348,10 @@ int sphb_destroy(sphb_ctx *c)
     cudaFree(c->scan.tile_state); cudaFree(c->scan.tile_counter); cudaFree(c->d_stats_done); cudaFree(c->d_step_slots);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stats) cudaFreeHost(c->h_stats);
-    for (int i = 0; i < 128; i++) cudaEventDestroy(c->ev[i]);
-    cudaStreamDestroy(c->stream);
+    for (int i = 0; i < 128; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
     delete c;
     return SPHB_OK;
 }
@@ -485,7 +501,12 @@ static int step_launch(sphb_ctx *c, float gx, float gy, const float *trace, int 
         if (c->mg.on) {
             step_phase_a(c, true, deliver);
             int rc = mg_exchange(c);
-            if (rc) return rc;
+            if (rc) {
+                // the ticket of this call is never delivered: take it back so the statistics path stays usable
+                // (no force pass has added to its slots yet: only the last step's does)
+                if (want_stats) { c->stats_seq--; if (ticket_out) *ticket_out = 0; }
+                return rc;
+            }
             step_phase_b(c, gx, gy, true, with_stats ? &ss : nullptr);
         } else {
             build_grid(c, c->fluid, true, nullptr, deliver);                   // :615-626
@@ -536,6 +557,7 @@ static int stats_collect(sphb_ctx *c, unsigned long long ticket, sphb_stats *sta
     decode_stats(c, &h, stats_out);
     stats_out->steps = c->stats_steps[ticket & 1ULL];     // the step count when these were requested
     c->stats_collected = ticket;
+    if (c->mg.on && (stats_out->n_overflow & (1u << 30))) { c->mg.comm_failed = true; return mg_health(c); }
     return SPHB_OK;
 }
 
@@ -583,7 +605,7 @@ int sphb_synchronize(sphb_ctx *c)
     SPHB_ENTER(c);
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
     SPHB_CUDA(cudaGetLastError());
-    return SPHB_OK;
+    return mg_health(c);
 }
 
 int sphb_download(sphb_ctx *c, sphb_particle *fluid_out, float *du_dt, float *dv_dt)
@@ -672,6 +694,32 @@ int sphb_neighbor_lists(sphb_ctx *c, int which, int cap, int *counts, int *lists
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
     SPHB_CUDA(cudaMemsetAsync(d_over, 0, sizeof(unsigned int), c->stream));
     return (int)over;
+}
+
+int sphb_handover_lists(sphb_ctx *c, int cap, int *counts, int *lists, unsigned int *n_whole_chunks)
+{
+    SPHB_ENTER(c);
+    if (cap <= 0 || !counts || !lists) return SPHB_E_ARG;
+    const ParticleSet &f = c->fluid;
+    if (f.n <= 0 || c->mg.on) { set_error("sphb_handover_lists: needs an uploaded single-GPU context"); return SPHB_E_STATE; }
+    if (!f.sorted || !f.lists_valid) { set_error("no handed-over lists: run sphb_compute_accel or sphb_step first"); return SPHB_E_STATE; }
+    const size_t cb = (((size_t)f.n + 3) & ~(size_t)3) * sizeof(int), lb = (size_t)f.n * cap * sizeof(int);
+    int rc = ensure_stage(c, cb + lb + 64);
+    if (rc) return rc;
+    int *d_counts = static_cast<int *>(c->d_stage);
+    int *d_lists = d_counts + (((size_t)f.n + 3) & ~(size_t)3);
+    unsigned int *d_fast = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(c->d_stage) + cb + lb);
+    SPHB_CUDA(cudaMemsetAsync(d_lists, 0xff, lb, c->stream));
+    SPHB_CUDA(cudaMemsetAsync(d_fast, 0, sizeof(unsigned int), c->stream));
+    c->launches += launch_decode_handover(c->stream, c->k, f, cap, d_counts, d_lists, d_fast);
+    unsigned int fast = 0;
+    SPHB_CUDA(cudaMemcpyAsync(counts, d_counts, (size_t)f.n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaMemcpyAsync(lists, d_lists, lb, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaMemcpyAsync(&fast, d_fast, sizeof fast, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    if (n_whole_chunks) *n_whole_chunks = fast;
+    return SPHB_OK;
 }
 
 int sphb_probe_force_pair(sphb_ctx *c, int n, const float *pairs, int variant, float *out_txy, int *exact_shortcuts)
@@ -809,6 +857,7 @@ int sphb_get_stats(sphb_ctx *c, sphb_stats *out)
     SPHB_CUDA(cudaMemcpyAsync(h, c->d_stats, sizeof(StatsBlock), cudaMemcpyDeviceToHost, c->stream));
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
     decode_stats(c, h, out);
+    if (c->mg.on && (out->n_overflow & (1u << 30))) { c->mg.comm_failed = true; return mg_health(c); }
     return SPHB_OK;
 }
 

@@ -136,6 +136,7 @@ struct ParticleSet {
     uint32_t *cell_count = nullptr;           // ncells, zero between builds
     uint32_t *cell_start = nullptr;           // ncells + 1
     bool sorted = false;
+    bool counters_dirty = false;              // a grid build ran since the density pass last published the build counters
     bool uniform_mass = true;
     // accepted-neighbour lists handed from the density pass to the force pass of the same step
     unsigned short *nbr_list = nullptr;       // [CTA][entry < kListCap][thread] tile byte offsets
@@ -163,9 +164,12 @@ struct ScanState {
     unsigned long long launches = 0;
 };
 
-struct DeviceCounters {        // lives in HBM, read back by sphb_get_stats
-    unsigned int n_escaped;
-    unsigned int max_cell_count;
+struct DeviceCounters {        // lives in HBM, read back by sphb_get_stats ([0] fluid builds, [1] boundary builds)
+    unsigned int n_escaped;        // particles binned by clamping at the LAST build    } published by the density pass
+    unsigned int max_cell_count;   // largest cell population at the last build          } that follows the build
+    unsigned int escaped_acc;      // running count the binning kernel adds to
+    unsigned int escaped_prev;     //   ... and its value at the previous publication
+    unsigned int max_cell_acc;     // running maximum of the scan since the previous publication
     unsigned int list_flushes;     // times a thread's accepted list filled up
     unsigned int tiles_unstaged;   // CTAs that fell back to global reads
     unsigned long long pair_candidates;
@@ -286,6 +290,7 @@ struct MgState {
     unsigned long long exchanges = 0;    // step parity for the double-buffered receive side
     unsigned long long halo_bytes = 0;   // bytes sent so far
     int n_uploaded = 0;                  // particles of the last sphb_mg_upload (slot order until the first sort)
+    bool comm_failed = false;            // a neighbour's message timed out (mg_health): every later call fails
 };
 
 }  // namespace sphb
@@ -366,6 +371,8 @@ int launch_density(cudaStream_t st, const Consts &k, ParticleSet &fluid, const P
 int launch_force(cudaStream_t st, const Consts &k, ParticleSet &fluid, const ParticleSet &boundary,
                  float gx, float gy, const float2 *g_dev, bool kick2, DeviceCounters *ctr,
                  bool allow_stage = true, const StepStats *stats = nullptr, bool fast_force = false);
+int launch_decode_handover(cudaStream_t st, const Consts &k, const ParticleSet &f, int cap, int *counts, int *lists,
+                           unsigned int *n_fast_chunks);
 int launch_probe_force_pair(cudaStream_t st, const Consts &k, int n, const float *in, int variant, float *out);
 int launch_neighbor_lists(cudaStream_t st, const Consts &k, const ParticleSet &a, const ParticleSet &b,
                           bool same, int cap, int *counts, int *lists, unsigned int *overflow);
@@ -392,6 +399,7 @@ int mg_exchange_nccl(sphb_ctx *c);
 int mg_exchange(sphb_ctx *c);            // the transport's part of a step between phase A and phase B
 int launch_halo_signal(cudaStream_t st, const SlabIO &io, uint32_t epoch);
 int mg_init_boundary(sphb_ctx *c);
+int mg_health(sphb_ctx *c);              // SPHB_E_COMM once a halo wait has timed out; call after a stream synchronise
 void mg_free(sphb_ctx *c);
 
 }  // namespace sphb

@@ -200,6 +200,26 @@ int mg_init_boundary(sphb_ctx *c)
     return SPHB_OK;
 }
 
+// A neighbour's message that never arrived (k_bin_recv gave up after its device-side time-out) makes the
+// slab's state wrong from that step on: fatal.  Called where the host has just synchronised the stream.
+int mg_health(sphb_ctx *c)
+{
+    MgState &m = c->mg;
+    if (!m.on || m.transport != 3 || !m.d_flags) return SPHB_OK;
+    if (!m.comm_failed) {
+        unsigned int flags[2] = {0u, 0u};
+        SPHB_CUDA(cudaMemcpyAsync(flags, m.d_flags, sizeof flags, cudaMemcpyDeviceToHost, c->stream));
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));
+        m.comm_failed = (flags[1] & (1u << 30)) != 0u;
+    }
+    if (m.comm_failed) {
+        set_error("rank %d of %d: a neighbour's halo/migration message did not arrive within the device-side time-out "
+                  "(peer-store transport); the state of this slab is invalid from that step on", m.rank, m.world);
+        return SPHB_E_COMM;
+    }
+    return SPHB_OK;
+}
+
 void mg_free(sphb_ctx *c)
 {
     MgState &m = c->mg;
@@ -515,6 +535,8 @@ int sphb_mg_download(sphb_ctx *c, int cap, sphb_particle *fluid_out, uint32_t *i
     SPHB_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, c->stream));
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
     *n_out = (int)n;
+    rc = mg_health(c);
+    if (rc) return rc;
     if ((int)n > cap) { set_error("%u owned particles exceed the caller's capacity %d", n, cap); return SPHB_E_ARG; }
     if (n > 0) {
         SPHB_CUDA(cudaMemcpyAsync(fluid_out, d_aos, (size_t)n * sizeof(sphb_particle), cudaMemcpyDeviceToHost, c->stream));

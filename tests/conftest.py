@@ -17,6 +17,7 @@ G = (0.0, -9.81)     # pi_sph_fluid.c:442-443
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run by `pytest -m gpu` on the GPU box)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 B200s (run by `pytest -m multigpu` under `gpurun --gpus 2`)")
 
 
 def _has_gpu() -> bool:
@@ -27,8 +28,24 @@ def _has_gpu() -> bool:
         return False
 
 
+def _gpu_count() -> int:
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
 def pytest_collection_modifyitems(config, items):
-    if _has_gpu():
+    ngpu = _gpu_count()
+    if ngpu < 2:
+        # tests that need two real devices are not part of a one-GPU (or CPU) session at all: they run under
+        # `gpurun --gpus 2 -- pytest -m multigpu` and their log is committed under profiles/
+        multi = [it for it in items if "multigpu" in it.keywords]
+        if multi:
+            items[:] = [it for it in items if "multigpu" not in it.keywords]
+            config.hook.pytest_deselected(items=multi)
+    if ngpu > 0:
         return
     skip = pytest.mark.skip(reason="no CUDA device here (GPU tests run under gpurun)")
     for item in items:

@@ -6,7 +6,10 @@ Every rank builds its slab of the scene, the ranks step together through sphb_st
 migration over ncclSend/ncclRecv, or — "ipc" — stored by the advect+bin kernel straight into the
 neighbour's receive buffer over NVLink and completed by a device-side signal), rank 0 gathers the
 owned particles and compares them BIT FOR BIT with a single-GPU run of the same scene.
-Prints "mg_nccl_check ok" / "mg_ipc_check ok"."""
+"ipc1dev": the same peer-store transport with every rank on CUDA device 0 — N processes sharing ONE GPU,
+receive blocks mapped across processes with cudaIpc*, handles carried by gloo, no NCCL anywhere — so the
+cross-process transport is testable on a one-GPU box.
+Prints "mg_nccl_check ok" / "mg_ipc_check ok" / "mg_ipc1dev_check ok"."""
 import os
 import sys
 from pathlib import Path
@@ -22,21 +25,28 @@ import pi_sph_fluid_b200 as pkg  # noqa: E402
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     transport = sys.argv[1] if len(sys.argv) > 1 else "nccl"
-    dev = int(os.environ.get("LOCAL_RANK", rank))
+    one_dev = transport == "ipc1dev"
+    dev = 0 if one_dev else int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
-    R, steps, g = 0.01, 600, (200.0, -9.81)    # strong sideways pull: particles cross the cuts (counted below)
+    if one_dev:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    # strong sideways pull: particles cross the cuts (counted below).  Processes sharing one device are
+    # time-sliced, and every step waits for the neighbour's signal: fewer steps there.
+    R, steps, g = 0.01, (150 if one_dev else 600), ((2000.0, -9.81) if one_dev else (200.0, -9.81))
     prm = pkg.default_params(R, device=dev)
     box = (2 * R, 1.5, 2 * R, 0.6)
     cuts = pkg.plan_cuts(pkg.scene_block_column_hist(prm, *box), world)
     boundary = pkg.scene_boundary(prm)
     part, base = pkg.scene_block_slab(prm, *box, int(cuts[rank]), int(cuts[rank + 1]))
 
-    ident = [pkg.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ident, src=0)
     slab = pkg.Slab(prm, rank, world, int(cuts[rank]), int(cuts[rank + 1]), halo_capacity=16384)
-    slab.connect_nccl(ident[0])
-    if transport == "ipc":
+    if not one_dev:
+        ident = [pkg.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        slab.connect_nccl(ident[0])
+    if transport in ("ipc", "ipc1dev"):
         handles = [None] * world
         dist.all_gather_object(handles, slab.ipc_handle())
         slab.connect_ipc(handles)
@@ -46,7 +56,16 @@ def main():
     slab.compute_accel(*g)
     slab.step(steps, *g)
     ids, f, du, dv = slab.download()
-    st = slab.allreduce_stats()
+    if one_dev:
+        per = [None] * world
+        dist.all_gather_object(per, slab.stats())
+        st = dict(per[0])
+        for q in per[1:]:
+            for key in ("n_fluid", "n_lost", "n_overflow", "kinetic"):
+                st[key] += q[key]
+            st["max_speed"] = max(st["max_speed"], q["max_speed"])
+    else:
+        st = slab.allreduce_stats()
     info = slab.info()
     gathered = [None] * world
     dist.all_gather_object(gathered, (ids, f, du, dv, base, len(part)))
@@ -74,9 +93,9 @@ def main():
         ok &= migrated > 0 or world == 1
         print(f"world {world} ({transport}): {len(full)} particles, {steps} steps, migrated {migrated}, owned-out-of-slab {moved}, "
               f"message {info['message_bytes']} B, sent {info['bytes_sent']} B, identical={ok}")
-    flag = torch.tensor([1 if ok else 0], device=f"cuda:{dev}")
+    flag = torch.tensor([1 if ok else 0]) if one_dev else torch.tensor([1 if ok else 0], device=f"cuda:{dev}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if transport == "ipc":
+    if transport in ("ipc", "ipc1dev"):
         slab.disconnect_ipc()          # unmap the neighbours' blocks on every rank before anybody frees its own
         dist.barrier()
     slab.close()

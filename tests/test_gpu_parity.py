@@ -109,6 +109,43 @@ def test_neighbour_lists_exact_and_in_reference_order(lib_built, golden075, gold
         sim.close()
 
 
+def test_handed_over_lists_are_the_reference_neighbour_lists(oracle_built, lib_built, golden075, golden02):
+    """The lists k_force actually consumes — the accepted tile offsets phase 1 of k_density (corner culling,
+    packed distance test, staged cell_start windows) hands over through HBM, decoded by sphb_handover_lists —
+    against the reference's find_neighbors (:126-153): same sets, same order.  Golden scenes first (lists
+    produced by the reference build), then a 61k-particle drop after 300 steps against the oracle."""
+    pkg = lib_built
+    for g, R, snap in ((golden075, 0.075, 0), (golden075, 0.075, 2000), (golden02, 0.02, 5000)):
+        sim = run_gpu(pkg, R, g[f"fluid_{snap}"], g["boundary_init"])
+        sim.compute_accel(*G)
+        counts, lists, whole = sim.handover_lists(cap=64)
+        off, flat = g[f"ff_off_{snap}"], g[f"ff_list_{snap}"]
+        handed = counts >= 0
+        assert handed.mean() > 0.95, (snap, handed.mean())          # the search-again path is the exception
+        assert np.array_equal(counts[handed], np.diff(off)[handed])
+        for i in np.nonzero(handed)[0]:
+            assert np.array_equal(lists[i, :counts[i]], flat[off[i]:off[i + 1]]), (snap, i)
+        sim.close()
+    R = 0.005
+    prm = pkg.default_params(R)
+    fluid, boundary = pkg.scene_drop(prm), pkg.scene_boundary(prm)
+    with pkg.Simulation(prm) as sim:
+        sim.upload(fluid, boundary); sim.init_boundary(); sim.compute_accel(*G)
+        sim.step(300, 3.0, -9.81)
+        f, du, dv = sim.download()
+        counts, lists, whole = sim.handover_lists(cap=64)
+    assert whole > 0.9 * (len(fluid) / 128)                          # most chunks are one staged part
+    o = oracle_built.Oracle(R=R, variant="chain")
+    gf = o.grid(len(f)); o.grid_update(gf, f)
+    handed = counts >= 0
+    assert handed.mean() > 0.99
+    rng = np.random.default_rng(1)
+    for i in rng.choice(len(f), 6000, replace=False):
+        ref = o.neighbor_list(f, f, int(i), gf, True)
+        if handed[i]:
+            assert counts[i] == len(ref) and np.array_equal(lists[i, :counts[i]], ref), i
+
+
 def test_operator_tier_against_reference_golden(lib_built, golden02, golden075):
     """Compat tier: each reference-named operator fed the reference's own arrays must return
     what the reference returned (fixtures built by the reference's compiled code)."""

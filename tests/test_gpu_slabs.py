@@ -4,8 +4,8 @@ The decomposition is exact by construction: in deterministic mode every owned pa
 same neighbours in the same order as in the single-GPU run, so the N-slab result must equal the
 1-GPU result BIT FOR BIT (positions, velocities, rho, p, accelerations), through halo exchange and
 migration.  The in-process transport runs any number of slabs on one device, so these tests need
-one GPU; tests/mg_nccl_check.py covers the NCCL transport on >= 2 GPUs (run under torchrun; the
-pytest wrapper below launches it when two devices are visible).
+one GPU; so does the cross-process peer-store (CUDA IPC) transport with several processes on device 0.
+tests/test_multigpu.py (marker `multigpu`, needs >= 2 GPUs) covers NCCL and IPC across real devices.
 """
 import os
 import subprocess
@@ -190,21 +190,19 @@ def test_slab_api_misuse(lib_built):
     s.close()
 
 
-@pytest.mark.parametrize("world,transport", [(2, "nccl"), (2, "ipc")])
-def test_process_per_gpu_transports_under_torchrun(lib_built, world, transport):
-    """One process per GPU: halo + migration over ncclSend/ncclRecv, and as peer stores into the
-    neighbour's receive buffer (CUDA IPC) completed by a device-side signal — both bit-identical to
-    the single-GPU run."""
-    import torch
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+@pytest.mark.parametrize("world", [2, 3])
+def test_cross_process_peer_store_transport_on_one_device(lib_built, world):
+    """The peer-store transport ACROSS PROCESSES on a one-GPU box: `world` processes share device 0, each maps
+    its neighbours' receive blocks with cudaIpc* (handles carried by gloo, no NCCL), k_advect_bin stores the
+    halo + migration entries into the neighbour process's buffer and k_bin_recv waits for the device-side
+    signal — bit-identical to the single-GPU run, with particles migrating between the processes."""
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                        "--master-addr", "127.0.0.1", "--master-port", "29631" if transport == "nccl" else "29633",
-                        str(ROOT / "tests" / "mg_nccl_check.py"), transport],
-                       capture_output=True, text=True, timeout=600, env=env)
+                        "--master-addr", "127.0.0.1", "--master-port", str(29640 + world),
+                        str(ROOT / "tests" / "mg_nccl_check.py"), "ipc1dev"],
+                       capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert f"mg_{transport}_check ok" in r.stdout
+    assert "mg_ipc1dev_check ok" in r.stdout
 
 
 def test_ipc_transport_single_process_loopback(lib_built):

@@ -1,0 +1,33 @@
+"""Transports of the slab path across REAL devices (>= 2 GPUs).  Not part of `pytest -m gpu` (the driver's box
+has one GPU): run as `pytest -m multigpu tests/test_multigpu.py` under `gpurun --gpus 2`; the log of that run
+is committed under profiles/.  The cross-process peer-store transport itself is also covered on one device by
+tests/test_gpu_slabs.py::test_cross_process_peer_store_transport_on_one_device."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.multigpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.parametrize("world,transport", [(2, "nccl"), (2, "ipc")])
+def test_process_per_gpu_transports_under_torchrun(lib_built, world, transport):
+    """One process per GPU (needs 2 GPUs: `pytest -m multigpu` under `gpurun --gpus 2`; the log of that run is
+    committed under profiles/): halo + migration over ncclSend/ncclRecv, and as peer stores into the
+    neighbour's receive buffer (CUDA IPC) completed by a device-side signal — both bit-identical to
+    the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631" if transport == "nccl" else "29633",
+                        str(ROOT / "tests" / "mg_nccl_check.py"), transport],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"mg_{transport}_check ok" in r.stdout
+
+
