@@ -194,7 +194,8 @@ int sphb_handover_lists(sphb_ctx *ctx, int cap, int *counts, int *lists, unsigne
  * made testable one pair at a time.  pairs: 12 floats each (x_i y_i x_j y_j | u_i v_i u_j v_j |
  * rho_i p_i/rho_i^2 rho_j p_j/rho_j^2), m_j = the uniform fluid mass; out: (tx, ty) per pair.
  * variant 0: the hot loop's form (packed, exact-division shortcuts), 1: general IEEE divisions,
- * 2: scalar form with the shortcuts; +4: j is a boundary particle (:346-365).  *exact_shortcuts says
+ * 2: scalar form with the shortcuts, 3: the hot loop's two-neighbours-at-once form (rows 2t and 2t+1 must
+ * carry the same particle i; n even); +4 on variants 0-2: j is a boundary particle (:346-365).  *exact_shortcuts says
  * whether the host verified the shortcuts for this context's H (variants 0, 2 are only then exact). */
 int sphb_probe_force_pair(sphb_ctx *ctx, int n, const float *pairs, int variant, float *out_txy, int *exact_shortcuts);
 

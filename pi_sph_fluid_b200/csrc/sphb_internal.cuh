@@ -31,7 +31,7 @@ constexpr int kStreamThreads = SPHB_STREAM_THREADS;   // advect/bin, reorder, ga
 #define SPHB_PERSISTENT 0
 #endif
 #ifndef SPHB_MINB_D
-#define SPHB_MINB_D 12
+#define SPHB_MINB_D 10
 #endif
 #ifndef SPHB_MINB_F
 #define SPHB_MINB_F 8

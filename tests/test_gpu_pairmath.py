@@ -48,6 +48,18 @@ def test_force_pair_sequences_bit_exact(lib_built, emu, R):
             assert np.isnan(ref[0]).all() and np.isfinite(ref[1:]).all()
             got, shortcuts = sim.probe_force_pair(pairs, 1 + 4 * boundary)
             assert same_bits_nan(got, ref), ("general", boundary, int((got.view("u4") != ref.view("u4")).sum()))
+            if shortcuts and not boundary:
+                # two neighbours at once: rows 2t and 2t+1 share particle i
+                two = pairs.copy()
+                for cols in (slice(0, 2), slice(4, 6), slice(8, 10)):
+                    two[1::2, cols] = two[0::2, cols]
+                # keep j inside the support of the shared i
+                two[1::2, 2:4] = two[1::2, 0:2] + (pairs[1::2, 2:4] - pairs[1::2, 0:2])
+                ref2 = np.zeros((len(two), 2), np.float32)
+                emu.emu_force_pair(C.byref(prm), len(two), two.ctypes.data_as(C.c_void_p), 0, ref2.ctypes.data_as(C.c_void_p))
+                got, _ = sim.probe_force_pair(two, 3)
+                bad = (got.view("u4") != ref2.view("u4")) & ~np.isnan(ref2)
+                assert same_bits_nan(got, ref2), ("two at once", int(bad.sum()), two[bad.any(axis=1)][:3], got[bad.any(axis=1)][:3], ref2[bad.any(axis=1)][:3])
             if shortcuts:
                 for variant in (0, 2):
                     got, _ = sim.probe_force_pair(pairs, variant + 4 * boundary)
