@@ -257,6 +257,13 @@ int sphb_grid_columns(const sphb_params *prm, int *rows, int *cols);
 int sphb_column_of(const sphb_params *prm, float x);
 int sphb_column_histogram(const sphb_params *prm, const sphb_particle *particles, int n, unsigned long long *hist);
 int sphb_mg_plan_cuts(const unsigned long long *hist, int cols, int world, int min_width, int *cuts /* world+1 */);
+/* the same with a cost per column on top of its particles, in particle units: what the (possibly empty)
+ * cells of a column cost a rank per step — the prefix scan walks every cell of the rank's window, measured
+ * 0.034 particle-equivalents per cell, i.e. column_cost = 0.034 * rows — so that a dam break's dry half is
+ * not one rank's burden.  column_cost = 0: plain particle-count quantiles. */
+#define SPHB_CELL_COST 0.034
+int sphb_mg_plan_cuts_cost(const unsigned long long *hist, int cols, int world, int min_width, double column_cost,
+                           int *cuts /* world+1 */);
 
 int sphb_mg_configure(sphb_ctx *ctx, int rank, int world, int col_lo, int col_hi,
                       int particle_capacity /* 0: 1.25 n + slack */, int halo_capacity /* 0: 65536 */);

@@ -129,6 +129,7 @@ def lib() -> C.CDLL:
         "sphb_column_of": (ci, [vp, cf]),
         "sphb_column_histogram": (ci, [vp, vp, ci, vp]),
         "sphb_mg_plan_cuts": (ci, [vp, ci, ci, ci, vp]),
+        "sphb_mg_plan_cuts_cost": (ci, [vp, ci, ci, ci, C.c_double, vp]),
         "sphb_mg_configure": (ci, [vp, ci, ci, ci, ci, ci, ci]),
         "sphb_mg_unique_id": (ci, [vp]),
         "sphb_mg_connect_nccl": (ci, [vp, vp]),
@@ -438,10 +439,15 @@ def columns_of(prm: Params, x: np.ndarray) -> np.ndarray:
     return np.fromiter((f(C.byref(prm), float(v)) for v in np.asarray(x, np.float32)), np.int32, len(x))
 
 
-def plan_cuts(hist: np.ndarray, world: int, min_width: int = 4) -> np.ndarray:
+CELL_COST = 0.034     # SPHB_CELL_COST: particle-equivalents per grid cell per step (the prefix scan)
+
+
+def plan_cuts(hist: np.ndarray, world: int, min_width: int = 4, column_cost: float = 0.0) -> np.ndarray:
+    """Cuts at the quantiles of particles-per-column (+ `column_cost` per column, e.g. CELL_COST * rows)."""
     hist = np.ascontiguousarray(hist, np.uint64)
     cuts = np.zeros(world + 1, np.int32)
-    _check(lib().sphb_mg_plan_cuts(_p(hist), len(hist), world, min_width, _p(cuts)), "sphb_mg_plan_cuts")
+    _check(lib().sphb_mg_plan_cuts_cost(_p(hist), len(hist), world, min_width, float(column_cost), _p(cuts)),
+           "sphb_mg_plan_cuts_cost")
     return cuts
 
 

@@ -148,21 +148,22 @@ int sphb_column_histogram(const sphb_params *prm, const sphb_particle *particles
 
 /* cuts[r] = first column of rank r: the columns are split at the particle-count quantiles, then
  * widened so that every slab has at least min_width columns */
-int sphb_mg_plan_cuts(const unsigned long long *hist, int cols, int world, int min_width, int *cuts)
+int sphb_mg_plan_cuts_cost(const unsigned long long *hist, int cols, int world, int min_width, double column_cost, int *cuts)
 {
-    if (!hist || !cuts || world < 1 || cols < 1) return SPHB_E_ARG;
+    if (!hist || !cuts || world < 1 || cols < 1 || !(column_cost >= 0.0)) return SPHB_E_ARG;
     if (min_width < 1) min_width = 1;
     if ((long long)world * min_width > cols) return SPHB_E_ARG;
-    unsigned long long total = 0;
-    for (int c = 0; c < cols; c++) total += hist[c];
+    /* cost of a column = its particles + what its (possibly empty) cells cost the scan, in particle units */
+    long double total = 0;
+    for (int c = 0; c < cols; c++) total += (long double)hist[c] + column_cost;
     cuts[0] = 0;
     cuts[world] = cols;
-    unsigned long long acc = 0;
+    long double acc = 0;
     int c = 0;
     for (int r = 1; r < world; r++) {
-        /* smallest cut with at least r/world of the particles to its left */
-        const unsigned long long want = (unsigned long long)(((long double)total * r) / world);
-        while (c < cols && acc < want) acc += hist[c++];
+        /* smallest cut with at least r/world of the cost to its left */
+        const long double want = total * r / world;
+        while (c < cols && acc < want) { acc += (long double)hist[c] + column_cost; c++; }
         cuts[r] = c;
     }
     for (int r = 1; r < world; r++)          /* forward: minimum width of slab r-1 */
@@ -170,6 +171,11 @@ int sphb_mg_plan_cuts(const unsigned long long *hist, int cols, int world, int m
     for (int r = world - 1; r >= 1; r--)     /* backward: minimum width of slab r */
         if (cuts[r] > cuts[r + 1] - min_width) cuts[r] = cuts[r + 1] - min_width;
     return SPHB_OK;
+}
+
+int sphb_mg_plan_cuts(const unsigned long long *hist, int cols, int world, int min_width, int *cuts)
+{
+    return sphb_mg_plan_cuts_cost(hist, cols, world, min_width, 0.0, cuts);
 }
 
 /* block scene restricted to the lattice columns whose x falls into cell columns [col_lo, col_hi):

@@ -31,6 +31,16 @@ def test_plan_cuts_properties(lib_built):
     assert (np.diff(cuts) >= 4).all() and cuts[-1] == 100
     with pytest.raises(pkg.SphbError):
         pkg.plan_cuts(np.ones(10, np.uint64), 4, 4)
+    # a cost per column (the cells a rank's scan walks): a dam break's dry half is shared out — the last rank
+    # gets fewer particles for its many empty columns, and the total cost per rank is level
+    hist = np.zeros(8703, np.uint64); hist[:4350] = 14700
+    plain = pkg.plan_cuts(hist, 8, 4)
+    cost = pkg.api.CELL_COST * 4352
+    fair = pkg.plan_cuts(hist, 8, 4, column_cost=cost)
+    assert plain[-2] < fair[-2] and fair[-1] == 8703       # the last cut moves right: fewer particles for the last rank
+    per = np.array([hist[fair[r]:fair[r + 1]].sum() + cost * (fair[r + 1] - fair[r]) for r in range(8)])
+    assert np.abs(per - per.mean()).max() <= 2 * (14700 + cost)
+    assert hist[fair[7]:].sum() < hist[plain[7]:].sum()
 
 
 def test_column_of_matches_the_reference_binning(lib_built, oracle_built, golden02):
