@@ -41,23 +41,6 @@ __device__ __forceinline__ void slab_append(bool want, uint32_t *cnt, const Halo
     }
 }
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 // SLAB (multi-GPU): slots in ghost columns are dropped (their owner sends them again); owned
 // particles within two columns of a cut — on either side of it, after the drift — are appended to
 // the message for that neighbour: it covers the neighbour's ghost columns and the particles that
@@ -111,27 +94,6 @@ k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *
         slab_append(to_left, io.send_cnt[0], io.send[0], p, v, my, io.overflow);
         slab_append(to_right, io.send_cnt[1], io.send[1], p, v, my, io.overflow);
         if (live && outside && !to_left && !to_right) atomicAdd(io.lost, 1u);
-        if (io.signal_epoch) {
-            // Peer-store transport: the entries above went straight into the neighbours' receive buffers.  The
-            // LAST CTA to get here completes both messages: it publishes (epoch << 32 | count) into each
-            // neighbour's header with a system-scope release store — after every CTA's entries, which each
-            // CTA orders before its arrival on the counter — and the neighbour's k_bin_recv waits for the epoch.
-            if (to_left || to_right) __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                if (atomicAdd(io.done, 1u) == gridDim.x - 1u) {
-                    *io.done = 0u;
-                    __threadfence_system();
-                    for (int side = 0; side < 2; side++)
-                        if (io.has[side]) {
-                            const uint32_t c = *reinterpret_cast<volatile uint32_t *>(io.send_cnt[side]);
-                            st_release_sys_u64(reinterpret_cast<unsigned long long *>(io.send[side].hdr()),
-                                               ((unsigned long long)io.signal_epoch << 32) | c);
-                        }
-                }
-            }
-        }
     }
 }
 
@@ -152,11 +114,27 @@ int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool ad
 }
 
 // ---- peer-store transport across processes: message completion on the device -------------------
-// The advect+bin kernel stores this rank's message entries into the neighbours' receive buffers (peer
-// memory over NVLink) and its last CTA publishes (epoch << 32 | count) into the neighbour's message header
-// with a system-scope release store, so the entries are visible there before the word is; the neighbour's
-// k_bin_recv waits for the epoch.  k_halo_signal is the same publication as a kernel of its own (kept for
-// SPHB_HALO_SIGNAL_KERNEL=1, the form measured in round 1).
+// The advect+bin kernel has stored this rank's message entries into the neighbours' receive buffers
+// (peer memory over NVLink).  This one-warp kernel follows it on the stream: lane `side` publishes
+// (epoch << 32 | count) into the neighbour's message header with a system-scope release store, so the
+// entries are visible there before the word is.  The neighbour's k_bin_recv waits for the epoch.
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(32)
 k_halo_signal(const SlabIO io, const uint32_t epoch)
 {

@@ -113,9 +113,6 @@ struct SlabIO {
     // peer stores across processes: the binning kernel waits until hdr()[1] of each receive buffer
     // carries this epoch (0: the message is complete by stream order, nothing to wait for)
     uint32_t wait_epoch = 0;
-    // ... and the advect+bin kernel's last CTA publishes this rank's (epoch, count) words itself
-    unsigned int *done = nullptr;                 // CTAs of the advect+bin kernel that have finished (left at zero)
-    uint32_t signal_epoch = 0;                    // 0: no signal from inside the kernel
 };
 
 // A sorted particle set: SoA in HBM, permanently ordered by cell (row-major, the
@@ -285,8 +282,7 @@ struct MgState {
     unsigned char *d_recv_block = nullptr;   // one allocation (one IPC handle): 4 messages, recv_stride apart
     size_t recv_stride = 0;
     unsigned char *ipc_peer_block[2] = {nullptr, nullptr};    // the neighbours' receive blocks mapped here
-    uint32_t *d_send_cnt = nullptr;      // 2 words (in-process transport; NCCL counts in the message header) + [2] the
-                                         //   advect+bin kernel's finished-CTA counter (peer-store transport)
+    uint32_t *d_send_cnt = nullptr;      // 2 words (in-process transport; NCCL counts in the message header)
     unsigned int *d_flags = nullptr;     // [0] lost, [1] overflow
     int *d_counts = nullptr;             // [0] n_cur, [1] n_in (fluid), [2] boundary n
     sphb_ctx *peer[2] = {nullptr, nullptr};

@@ -91,14 +91,6 @@ size_t msg_bytes(int cap) { return 16 + (size_t)cap * 20; }
 
 }  // namespace
 
-// SPHB_HALO_SIGNAL_KERNEL=1: publish the message counts from a one-warp kernel after the advect+bin kernel
-// instead of from that kernel's last CTA
-static bool signal_kernel()
-{
-    static const bool on = [] { const char *e = getenv("SPHB_HALO_SIGNAL_KERNEL"); return e && *e && *e != '0'; }();
-    return on;
-}
-
 SlabIO mg_slab_io(const sphb_ctx *c)
 {
     const MgState &m = c->mg;
@@ -132,10 +124,6 @@ SlabIO mg_slab_io(const sphb_ctx *c)
     io.capacity = m.capacity;
     // every rank makes the same number of exchanges, so the count doubles as the message's epoch
     io.wait_epoch = m.transport == 3 ? (uint32_t)(m.exchanges + 1ULL) : 0u;
-    if (m.transport == 3 && m.world > 1 && !signal_kernel()) {
-        io.done = m.d_send_cnt + 2;
-        io.signal_epoch = io.wait_epoch;
-    }
     return io;
 }
 
@@ -169,7 +157,7 @@ static int mg_exchange_ipc(sphb_ctx *c)
     MgState &m = c->mg;
     if (m.world == 1) return SPHB_OK;
     const SlabIO io = mg_slab_io(c);
-    if (!io.signal_epoch) c->launches += launch_halo_signal(c->stream, io, io.wait_epoch);
+    c->launches += launch_halo_signal(c->stream, io, io.wait_epoch);
     for (int side = 0; side < 2; side++)
         if (io.has[side]) m.halo_bytes += 8;      // the entries themselves are counted on the device only
     return SPHB_OK;
@@ -300,8 +288,8 @@ int sphb_mg_configure(sphb_ctx *c, int rank, int world, int col_lo, int col_hi, 
             SPHB_CUDA(cudaMemset(m.d_recv[s][q], 0, 16));
         }
     }
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_send_cnt), 4 * sizeof(uint32_t)));
-    SPHB_CUDA(cudaMemset(m.d_send_cnt, 0, 4 * sizeof(uint32_t)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_send_cnt), 2 * sizeof(uint32_t)));
+    SPHB_CUDA(cudaMemset(m.d_send_cnt, 0, 2 * sizeof(uint32_t)));
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_flags), 2 * sizeof(unsigned int)));
     SPHB_CUDA(cudaMemset(m.d_flags, 0, 2 * sizeof(unsigned int)));
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_counts), 4 * sizeof(int)));
