@@ -297,6 +297,27 @@ int sphb_mg_upload_accel(sphb_ctx *ctx, const float *du_dt, const float *dv_dt);
 int sphb_mg_download(sphb_ctx *ctx, int cap, sphb_particle *fluid_out, uint32_t *ids_out, float *du_dt,
                      float *dv_dt, int *n_out);
 
+/* Re-cut of a RUNNING multi-process simulation (a dam break drains the left slabs, so cuts made
+ * at t = 0 go stale).  Collective: every rank calls it after the same step.  The ranks' per-column particle
+ * counts are summed, every rank plans the same new cuts (quantiles of particles + column_cost per column, as
+ * sphb_mg_plan_cuts_cost) and every particle — position, velocity, du_dt/dv_dt, global id — moves to the rank
+ * that owns its column now, in one grouped exchange; windows, slots and the windowed boundary are rebuilt and
+ * the run continues bit-identically (the peer-store halo transport, if connected, stays as it is).
+ * min_imbalance > 0: nothing happens while max/mean of the ranks' particle counts is <= it (e.g. 1.05).
+ * *changed_out: 1 when the cuts moved.
+ *   sphb_mg_rebalance       moves the bytes with ncclAllReduce / ncclSend / ncclRecv (sphb_mg_connect_nccl first);
+ *   sphb_mg_rebalance_host  lets the host program carry them (MPI, gloo, ...): `allreduce` sums `count` 64-bit
+ *                           words in place over all ranks; `alltoallv` sends send_bytes[r] bytes at send + send_off[r]
+ *                           to rank r and receives recv_bytes[r] bytes from rank r at recv + recv_off[r] (its own
+ *                           segment included); both return 0 on success.  Buffers are host memory. */
+typedef int (*sphb_mg_allreduce_u64_fn)(void *user, unsigned long long *inout, int count);
+typedef int (*sphb_mg_alltoallv_fn)(void *user, const void *send, const unsigned long long *send_bytes,
+                                    const unsigned long long *send_off, void *recv, const unsigned long long *recv_bytes,
+                                    const unsigned long long *recv_off);
+int sphb_mg_rebalance(sphb_ctx *ctx, int min_width, double column_cost, double min_imbalance, int *changed_out);
+int sphb_mg_rebalance_host(sphb_ctx *ctx, int min_width, double column_cost, double min_imbalance,
+                           sphb_mg_allreduce_u64_fn allreduce, sphb_mg_alltoallv_fn alltoallv, void *user, int *changed_out);
+
 int sphb_mg_group_compute_accel(sphb_ctx **ctxs, int n, float gravity_x, float gravity_y);
 /* gravity_xy: NULL (constant gravity_x/y) or nsteps (gx, gy) pairs */
 int sphb_mg_group_step(sphb_ctx **ctxs, int n, float gravity_x, float gravity_y, const float *gravity_xy, int nsteps);

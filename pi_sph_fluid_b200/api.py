@@ -146,6 +146,8 @@ def lib() -> C.CDLL:
         "sphb_mg_merge_stats": (ci, [vp, ci, vp]),
         "sphb_mg_allreduce_stats": (ci, [vp, vp]),
         "sphb_mg_info": (ci, [vp, vp]),
+        "sphb_mg_rebalance": (ci, [vp, ci, C.c_double, C.c_double, vp]),
+        "sphb_mg_rebalance_host": (ci, [vp, ci, C.c_double, C.c_double, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -538,6 +540,49 @@ class Slab(Simulation):
         _check(lib().sphb_mg_download(self._h, len(fluid), _p(_particles(fluid)), _p(ids), _p(du), _p(dv), C.byref(n)),
                "sphb_mg_download")
         return n.value
+
+    def rebalance(self, min_width: int = 4, column_cost: float = 0.0, min_imbalance: float = 0.0) -> bool:
+        """sphb_mg_rebalance (collective, NCCL): re-cut the running slabs at the current quantiles; True if the cuts moved."""
+        changed = C.c_int(0)
+        _check(lib().sphb_mg_rebalance(self._h, min_width, float(column_cost), float(min_imbalance), C.byref(changed)),
+               "sphb_mg_rebalance")
+        return bool(changed.value)
+
+    def rebalance_host(self, dist, min_width: int = 4, column_cost: float = 0.0, min_imbalance: float = 0.0) -> bool:
+        """sphb_mg_rebalance_host with the bytes carried by a torch.distributed process group of CPU tensors
+        (gloo): the same re-cut for host programs without NCCL between the ranks."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        @C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int)
+        def allreduce(_user, buf, count):
+            a = np.ctypeslib.as_array(buf, shape=(count,))
+            t = torch.from_numpy(a.view(np.int64))
+            dist.all_reduce(t)
+            return 0
+
+        @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_void_p,
+                     C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong))
+        def alltoallv(_user, send, sbytes, soff, recv, rbytes, roff):
+            def view(base, off, nbytes):
+                return torch.from_numpy(np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(base + off)))
+            if sbytes[rank]:
+                C.memmove(recv + roff[rank], send + soff[rank], sbytes[rank])
+            reqs = []
+            for r in range(world):
+                if r != rank and rbytes[r]:
+                    reqs.append(dist.irecv(view(recv, roff[r], rbytes[r]), src=r))
+            for r in range(world):
+                if r != rank and sbytes[r]:
+                    reqs.append(dist.isend(view(send, soff[r], sbytes[r]), dst=r))
+            for q in reqs:
+                q.wait()
+            return 0
+
+        changed = C.c_int(0)
+        _check(lib().sphb_mg_rebalance_host(self._h, min_width, float(column_cost), float(min_imbalance), allreduce, alltoallv,
+                                            None, C.byref(changed)), "sphb_mg_rebalance_host")
+        return bool(changed.value)
 
     def allreduce_stats(self) -> dict:
         st = Stats()

@@ -149,7 +149,9 @@ int launch_stats(cudaStream_t st, const Consts &k, const ParticleSet &f, double 
     if (grid > 148 * 4) grid = 148 * 4;
     const uint32_t last_id = f.windowed ? 0xffffffffu : (uint32_t)(f.n - 1);
     k_stats<<<grid, 256, 0, st>>>(k, f.cur(), last_id, f.vel[f.vc], f.rho_prr, f.uniform_mass ? nullptr : f.mass[f.mc],
-                                  f.uniform_mass_value, f.id[f.ic], f.windowed ? f.cellkey : nullptr, out_d,
+                                  f.uniform_mass_value, f.id[f.ic],
+                                  // an unsorted slab set (just uploaded or re-cut) holds owned particles only: no ghost slots yet
+                                  (f.windowed && f.sorted) ? f.cellkey : nullptr, out_d,
                                   reinterpret_cast<unsigned int *>(out_u), ctr, flags);
     return 1;
 }

@@ -597,6 +597,75 @@ int launch_pack_owned(cudaStream_t st, const Consts &k, const ParticleSet &ps, i
     return 1;
 }
 
+// ---- re-cut of the slabs (sphb_mg_rebalance) ------------------------------------------------------
+
+__global__ void __launch_bounds__(kStreamThreads)
+k_column_hist(const Consts k, const Count cnt, const uint32_t *__restrict__ cellkey, unsigned long long *__restrict__ hist)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (s >= count_of(cnt)) return;
+    const int col = (int)(cellkey[s] & 0xffffu);
+    if (owned_col(k, col)) atomicAdd(&hist[col + k.col_off], 1ULL);
+}
+
+int launch_column_hist(cudaStream_t st, const Consts &k, const ParticleSet &ps, unsigned long long *hist)
+{
+    if (ps.n == 0) return 0;
+    k_column_hist<<<(ps.n + kStreamThreads - 1) / kStreamThreads, kStreamThreads, 0, st>>>(k, ps.cur(), ps.cellkey, hist);
+    return 1;
+}
+
+// every owned particle as one 32-byte record in the segment of the rank that owns its column under the NEW
+// cuts (order inside a segment is arrival order: the next grid build restores ascending global id per cell)
+__global__ void __launch_bounds__(kStreamThreads)
+k_pack_by_dest(const Consts k, const Count cnt, const float2 *__restrict__ pos, const float2 *__restrict__ vel,
+               const float2 *__restrict__ acc, const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellkey,
+               const int *__restrict__ cuts, const int world, const unsigned long long *__restrict__ seg_off,
+               unsigned long long *__restrict__ cursor, MoveRec *__restrict__ out)
+{
+    const int s = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (s >= count_of(cnt)) return;
+    const int col = (int)(cellkey[s] & 0xffffu);
+    if (!owned_col(k, col)) return;
+    const int gcol = col + k.col_off;
+    int dest = 0;
+    while (dest + 1 < world && gcol >= cuts[dest + 1]) ++dest;
+    const unsigned long long i = seg_off[dest] + atomicAdd(&cursor[dest], 1ULL);
+    MoveRec r;
+    r.pos = pos[s]; r.vel = vel[s]; r.acc = acc[s]; r.id = id[s]; r.pad = 0u;
+    out[i] = r;
+}
+
+int launch_pack_by_dest(cudaStream_t st, const Consts &k, const ParticleSet &ps, const int *cuts_dev, int world,
+                        const unsigned long long *seg_off_dev, unsigned long long *cursor_dev, MoveRec *out)
+{
+    if (ps.n == 0) return 0;
+    k_pack_by_dest<<<(ps.n + kStreamThreads - 1) / kStreamThreads, kStreamThreads, 0, st>>>(
+        k, ps.cur(), ps.pos[ps.pc], ps.vel[ps.vc], ps.acc, ps.id[ps.ic], ps.cellkey, cuts_dev, world, seg_off_dev, cursor_dev, out);
+    return 1;
+}
+
+__global__ void __launch_bounds__(kStreamThreads)
+k_unpack_moved(const int n, const MoveRec *__restrict__ in, float2 *__restrict__ pos, float2 *__restrict__ vel,
+               float2 *__restrict__ acc, uint32_t *__restrict__ id)
+{
+    const int i = blockIdx.x * kStreamThreads + threadIdx.x;
+    if (i >= n) return;
+    const MoveRec r = in[i];
+    pos[i] = r.pos; vel[i] = r.vel; acc[i] = r.acc; id[i] = r.id;
+}
+
+// the set becomes `n` unsorted particles (slot order = record order), as after an upload
+int launch_unpack_moved(cudaStream_t st, ParticleSet &ps, const MoveRec *in, int n)
+{
+    ps.pc = ps.vc = ps.ic = ps.mc = ps.xc = 0;
+    ps.sorted = false;
+    ps.lists_valid = false;
+    if (n == 0) return 0;
+    k_unpack_moved<<<(n + kStreamThreads - 1) / kStreamThreads, kStreamThreads, 0, st>>>(n, in, ps.pos[0], ps.vel[0], ps.acc, ps.id[0]);
+    return 1;
+}
+
 // du_dt/dv_dt in original order -> acc[] in the set's current order
 __global__ void __launch_bounds__(kStreamThreads)
 k_set_accel(const int n, const uint32_t *__restrict__ id, const float *__restrict__ du,

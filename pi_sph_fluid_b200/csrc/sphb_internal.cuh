@@ -291,6 +291,8 @@ struct MgState {
     unsigned long long halo_bytes = 0;   // bytes sent so far
     int n_uploaded = 0;                  // particles of the last sphb_mg_upload (slot order until the first sort)
     bool comm_failed = false;            // a neighbour's message timed out (mg_health): every later call fails
+    int bnd_n_global = 0;                // wall particles of the whole tank: they stay, psi computed, in the buffers the
+                                         //   windowed sort read from, so a re-cut can window them again (sphb_mg_rebalance)
 };
 
 }  // namespace sphb
@@ -362,6 +364,13 @@ int launch_pack_owned(cudaStream_t st, const Consts &k, const ParticleSet &ps, i
 int launch_soa_to_aos(cudaStream_t st, const ParticleSet &ps, sphb_particle *aos, float *du, float *dv, bool is_boundary);
 int launch_set_accel(cudaStream_t st, ParticleSet &ps, const float *du, const float *dv, int n_slots = -1);
 int launch_cell_ids(cudaStream_t st, const Consts &k, const ParticleSet &ps, int *cell_out);
+// re-cut of the slabs (sphb_mg_rebalance): per-global-column counts of the owned particles; the owned particles
+// as 32-byte records grouped by destination rank; records back into an unsorted set
+struct MoveRec { float2 pos, vel, acc; uint32_t id, pad; };
+int launch_column_hist(cudaStream_t st, const Consts &k, const ParticleSet &ps, unsigned long long *hist);
+int launch_pack_by_dest(cudaStream_t st, const Consts &k, const ParticleSet &ps, const int *cuts_dev, int world,
+                        const unsigned long long *seg_off_dev, unsigned long long *cursor_dev, MoveRec *out);
+int launch_unpack_moved(cudaStream_t st, ParticleSet &ps, const MoveRec *in, int n);
 
 // ---- kernel launchers (kernels_pair.cu) ----------------------------------------------------
 int launch_pseudomass(cudaStream_t st, const Consts &k, ParticleSet &boundary);

@@ -171,6 +171,30 @@ int mg_exchange(sphb_ctx *c)
 // :600-601 on a slab.  psi needs every boundary neighbour, so it is computed once on the whole
 // tank's grid (the boundary is replicated and small); then the boundary is re-sorted on the
 // rank's window, which drops the wall particles no owned or ghost cell can see.
+// the boundary set as it stands (the whole tank's wall particles, psi computed, sorted on the tank's grid)
+// re-sorted on this rank's window; the sort reads those buffers and writes the other pair, so the whole set
+// survives there for the next re-cut
+static int mg_window_boundary(sphb_ctx *c)
+{
+    MgState &m = c->mg;
+    ParticleSet &b = c->boundary;
+    int n = b.n = m.bnd_n_global;
+    const int both[2] = {n, n};
+    SPHB_CUDA(cudaMemcpyAsync(m.d_counts + 2, both, sizeof both, cudaMemcpyHostToDevice, c->stream));
+    b.windowed = true;
+    b.d_n_cur = m.d_counts + 2;         // the scan replaces it by the number kept
+    b.d_n_in = m.d_counts + 3;          // the reorder still walks all n inputs
+    b.sorted = false;                       // keys of the global grid do not apply to the window
+    build_grid(c, b, false, &c->k);
+    SPHB_CUDA(cudaMemcpyAsync(&n, m.d_counts + 2, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    b.n = n;
+    b.d_n_cur = nullptr;
+    b.d_n_in = nullptr;
+    if (n == 0) b.sorted = false;
+    return SPHB_OK;
+}
+
 int mg_init_boundary(sphb_ctx *c)
 {
     MgState &m = c->mg;
@@ -180,20 +204,9 @@ int mg_init_boundary(sphb_ctx *c)
         b.d_n_cur = nullptr;
         build_grid(c, b, false, &m.k_global);
         c->launches += launch_pseudomass(c->stream, m.k_global, b);
-        int n = b.n;
-        const int both[2] = {n, n};
-        SPHB_CUDA(cudaMemcpyAsync(m.d_counts + 2, both, sizeof both, cudaMemcpyHostToDevice, c->stream));
-        b.windowed = true;
-        b.d_n_cur = m.d_counts + 2;         // the scan replaces it by the number kept
-        b.d_n_in = m.d_counts + 3;          // the reorder still walks all n inputs
-        b.sorted = false;                       // keys of the global grid do not apply to the window
-        build_grid(c, b, false, &c->k);
-        SPHB_CUDA(cudaMemcpyAsync(&n, m.d_counts + 2, sizeof n, cudaMemcpyDeviceToHost, c->stream));
-        SPHB_CUDA(cudaStreamSynchronize(c->stream));
-        b.n = n;
-        b.d_n_cur = nullptr;
-        b.d_n_in = nullptr;
-        if (n == 0) b.sorted = false;
+        m.bnd_n_global = b.n;
+        int rc = mg_window_boundary(c);
+        if (rc) return rc;
     }
     c->boundary_ready = true;
     SPHB_CUDA(cudaGetLastError());
@@ -235,6 +248,220 @@ void mg_free(sphb_ctx *c)
     m = MgState();
 }
 
+}  // namespace sphb
+
+// ---- re-cut across processes ("re-cut every K steps") ----------------------------------------
+// A dam break drains the left slabs: cuts made at t = 0 go stale.  sphb_mg_rebalance is collective — every
+// rank calls it after the same step: the per-column counts of all ranks are summed (one all-reduce; the old
+// cuts ride in the same buffer), every rank plans the same new cuts from them and, from the same histogram,
+// knows how many particles go from every rank to every other, so the particles (position, velocity,
+// du_dt/dv_dt, global id: 32 bytes each) travel in ONE grouped exchange with no count handshake.  The rank
+// then holds its new particles as an unsorted set — the state sphb_mg_upload + sphb_mg_upload_accel leave —
+// on the window of its new columns, and the run continues bit-identically.
+
+namespace sphb {
+namespace {
+
+struct Exchange {                        // how bytes travel between the ranks of this run
+    bool nccl = true;
+    sphb_mg_allreduce_u64_fn ar = nullptr;
+    sphb_mg_alltoallv_fn a2a = nullptr;
+    void *user = nullptr;
+};
+
+// d_buf: this rank's values -> h_buf: the sums over all ranks
+int xch_allreduce(sphb_ctx *c, const Exchange &x, unsigned long long *d_buf, unsigned long long *h_buf, int count)
+{
+    if (x.nccl) {
+        SPHB_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, ncclUint64, ncclSum, static_cast<ncclComm_t>(c->mg.nccl_comm), c->stream));
+        SPHB_CUDA(cudaMemcpyAsync(h_buf, d_buf, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));
+        return SPHB_OK;
+    }
+    SPHB_CUDA(cudaMemcpyAsync(h_buf, d_buf, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    if (x.ar(x.user, h_buf, count) != 0) { set_error("sphb_mg_rebalance_host: the all-reduce callback failed"); return SPHB_E_COMM; }
+    return SPHB_OK;
+}
+
+// counts and offsets in records; segment r of d_send goes to rank r, segment r of d_recv comes from rank r
+int xch_alltoallv(sphb_ctx *c, const Exchange &x, const MoveRec *d_send, const unsigned long long *scnt,
+                  const unsigned long long *soff, MoveRec *d_recv, const unsigned long long *rcnt, const unsigned long long *roff)
+{
+    const MgState &m = c->mg;
+    if (x.nccl) {
+        ncclComm_t comm = static_cast<ncclComm_t>(m.nccl_comm);
+        if (scnt[m.rank])
+            SPHB_CUDA(cudaMemcpyAsync(d_recv + roff[m.rank], d_send + soff[m.rank], (size_t)scnt[m.rank] * sizeof(MoveRec),
+                                      cudaMemcpyDeviceToDevice, c->stream));
+        SPHB_NCCL(g_nccl.GroupStart());
+        for (int r = 0; r < m.world; r++) {
+            if (r == m.rank) continue;
+            if (scnt[r]) SPHB_NCCL(g_nccl.Send(d_send + soff[r], (size_t)scnt[r] * sizeof(MoveRec), ncclUint8, r, comm, c->stream));
+            if (rcnt[r]) SPHB_NCCL(g_nccl.Recv(d_recv + roff[r], (size_t)rcnt[r] * sizeof(MoveRec), ncclUint8, r, comm, c->stream));
+        }
+        SPHB_NCCL(g_nccl.GroupEnd());
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));
+        return SPHB_OK;
+    }
+    // host-carried: stage both sides through pinned memory and hand byte counts to the caller's exchange
+    unsigned long long ns = 0, nr = 0;
+    for (int r = 0; r < m.world; r++) { ns += scnt[r]; nr += rcnt[r]; }
+    void *h_send = nullptr, *h_recv = nullptr;
+    SPHB_CUDA(cudaMallocHost(&h_send, (size_t)(ns ? ns : 1) * sizeof(MoveRec)));
+    cudaError_t e = cudaMallocHost(&h_recv, (size_t)(nr ? nr : 1) * sizeof(MoveRec));
+    if (e != cudaSuccess) { cudaFreeHost(h_send); SPHB_CUDA(e); }
+    int rc = SPHB_OK;
+    unsigned long long *bytes = static_cast<unsigned long long *>(malloc(sizeof(unsigned long long) * 4 * (size_t)m.world));
+    if (!bytes) rc = SPHB_E_NOMEM;
+    if (!rc) {
+        for (int r = 0; r < m.world; r++) {
+            bytes[r] = scnt[r] * sizeof(MoveRec); bytes[m.world + r] = soff[r] * sizeof(MoveRec);
+            bytes[2 * m.world + r] = rcnt[r] * sizeof(MoveRec); bytes[3 * m.world + r] = roff[r] * sizeof(MoveRec);
+        }
+        e = cudaMemcpyAsync(h_send, d_send, (size_t)ns * sizeof(MoveRec), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "staging the send buffer", __FILE__, __LINE__);
+    }
+    if (!rc && x.a2a(x.user, h_send, bytes, bytes + m.world, h_recv, bytes + 2 * m.world, bytes + 3 * m.world) != 0) {
+        set_error("sphb_mg_rebalance_host: the all-to-all callback failed");
+        rc = SPHB_E_COMM;
+    }
+    if (!rc) {
+        e = cudaMemcpyAsync(d_recv, h_recv, (size_t)nr * sizeof(MoveRec), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "staging the receive buffer", __FILE__, __LINE__);
+    }
+    free(bytes);
+    cudaFreeHost(h_send); cudaFreeHost(h_recv);
+    return rc;
+}
+
+struct DevBufs {                         // scratch of one re-cut, freed on every path
+    unsigned long long *hist = nullptr, *segoff = nullptr, *cursor = nullptr;
+    int *cuts = nullptr;
+    MoveRec *send = nullptr, *recv = nullptr;
+    ~DevBufs() { cudaFree(hist); cudaFree(segoff); cudaFree(cursor); cudaFree(cuts); cudaFree(send); cudaFree(recv); }
+};
+
+int rebalance_impl(sphb_ctx *c, int min_width, double column_cost, double min_imbalance, const Exchange &x, int *changed_out)
+{
+    MgState &m = c->mg;
+    if (changed_out) *changed_out = 0;
+    if (!m.on) { set_error("not a slab context"); return SPHB_E_STATE; }
+    if (!c->fluid.sorted || !c->accel_ready) { set_error("re-cut needs a stepped state (sphb_compute_accel / sphb_step first)"); return SPHB_E_STATE; }
+    if (m.world == 1) return SPHB_OK;
+    if (x.nccl && !m.nccl_comm) { set_error("sphb_mg_rebalance moves particles over NCCL: sphb_mg_connect_nccl first (or use sphb_mg_rebalance_host)"); return SPHB_E_STATE; }
+    if (m.transport == 2) { set_error("in-process groups re-cut through sphb_mg_download / sphb_mg_upload"); return SPHB_E_STATE; }
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    int rc = mg_health(c);
+    if (rc) return rc;
+    const int world = m.world, gcols = m.k_global.cols, count = gcols + world;
+    DevBufs d;
+    unsigned long long *h = static_cast<unsigned long long *>(calloc((size_t)count + 6 * (size_t)world + 8, sizeof(unsigned long long)));
+    int *cuts_old = static_cast<int *>(malloc(sizeof(int) * 2 * ((size_t)world + 1)));
+    if (!h || !cuts_old) { free(h); free(cuts_old); return SPHB_E_NOMEM; }
+    int *cuts_new = cuts_old + world + 1;
+    unsigned long long *scnt = h + count, *soff = scnt + world, *rcnt = soff + world, *roff = rcnt + world, *own = roff + world;
+    struct Free { void *a, *b; ~Free() { free(a); free(b); } } fr{h, cuts_old};
+
+    // 1. per-column counts of every rank, summed; the old cuts ride behind them
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d.hist), (size_t)count * 8));
+    SPHB_CUDA(cudaMemsetAsync(d.hist, 0, (size_t)count * 8, c->stream));
+    c->launches += launch_column_hist(c->stream, c->k, c->fluid, d.hist);
+    const unsigned long long my_lo = (unsigned long long)m.col_lo;
+    SPHB_CUDA(cudaMemcpyAsync(d.hist + gcols + m.rank, &my_lo, 8, cudaMemcpyHostToDevice, c->stream));
+    rc = xch_allreduce(c, x, d.hist, h, count);
+    if (rc) return rc;
+    for (int r = 0; r < world; r++) cuts_old[r] = (int)h[gcols + r];
+    cuts_old[world] = gcols;
+    if (cuts_old[m.rank] != m.col_lo || cuts_old[m.rank + 1] != m.col_hi) {
+        set_error("rank %d: the ranks disagree about the current cuts (was sphb_mg_rebalance called on every rank after the same step?)", m.rank);
+        return SPHB_E_COMM;
+    }
+    unsigned long long total = 0, most = 0;
+    for (int r = 0; r < world; r++) {
+        own[r] = 0;
+        for (int col = cuts_old[r]; col < cuts_old[r + 1]; col++) own[r] += h[col];
+        total += own[r];
+        most = own[r] > most ? own[r] : most;
+    }
+    if (min_imbalance > 0.0 && total > 0 && (double)most * world <= min_imbalance * (double)total) return SPHB_OK;
+
+    // 2. the new cuts (every rank computes the same)
+    rc = sphb_mg_plan_cuts_cost(h, gcols, world, min_width < 4 ? 4 : min_width, column_cost, cuts_new);
+    if (rc) { set_error("cannot cut %d columns into %d slabs", gcols, world); return rc; }
+    bool same = true;
+    for (int r = 0; r <= world; r++) same = same && cuts_new[r] == cuts_old[r];
+    if (same) return SPHB_OK;
+
+    // 3. who sends how much to whom follows from the histogram: no count handshake
+    unsigned long long n_send = 0, n_new = 0;
+    for (int r = 0; r < world; r++) {
+        scnt[r] = rcnt[r] = 0;
+        const int slo = cuts_new[r] > m.col_lo ? cuts_new[r] : m.col_lo, shi = cuts_new[r + 1] < m.col_hi ? cuts_new[r + 1] : m.col_hi;
+        for (int col = slo; col < shi; col++) scnt[r] += h[col];
+        const int rlo = cuts_old[r] > cuts_new[m.rank] ? cuts_old[r] : cuts_new[m.rank];
+        const int rhi = cuts_old[r + 1] < cuts_new[m.rank + 1] ? cuts_old[r + 1] : cuts_new[m.rank + 1];
+        for (int col = rlo; col < rhi; col++) rcnt[r] += h[col];
+        soff[r] = n_send; roff[r] = n_new;
+        n_send += scnt[r]; n_new += rcnt[r];
+    }
+    if (n_send != own[m.rank]) { set_error("rank %d: histogram and owned count disagree", m.rank); return SPHB_E_STATE; }
+    if (n_new > 2000000000ULL) { set_error("rank %d would own %llu particles", m.rank, n_new); return SPHB_E_ARG; }
+
+    // 4. pack by destination, exchange
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d.send), (size_t)(n_send ? n_send : 1) * sizeof(MoveRec)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d.recv), (size_t)(n_new ? n_new : 1) * sizeof(MoveRec)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d.cuts), sizeof(int) * ((size_t)world + 1)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d.segoff), 8 * (size_t)world));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d.cursor), 8 * (size_t)world));
+    SPHB_CUDA(cudaMemcpyAsync(d.cuts, cuts_new, sizeof(int) * ((size_t)world + 1), cudaMemcpyHostToDevice, c->stream));
+    SPHB_CUDA(cudaMemcpyAsync(d.segoff, soff, 8 * (size_t)world, cudaMemcpyHostToDevice, c->stream));
+    SPHB_CUDA(cudaMemsetAsync(d.cursor, 0, 8 * (size_t)world, c->stream));
+    c->launches += launch_pack_by_dest(c->stream, c->k, c->fluid, d.cuts, world, d.segoff, d.cursor, d.send);
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    rc = xch_alltoallv(c, x, d.send, scnt, soff, d.recv, rcnt, roff);
+    if (rc) return rc;
+
+    // 5. this rank's new slab: window, slots, particles, boundary
+    m.col_lo = cuts_new[m.rank];
+    m.col_hi = cuts_new[m.rank + 1];
+    const int win_lo = m.rank > 0 ? m.col_lo - 2 : 0, win_hi = m.rank < world - 1 ? m.col_hi + 2 : gcols;
+    Consts k2 = m.k_global;
+    k2.mass = c->k.mass;
+    set_window(k2, win_lo, win_hi, m.col_lo, m.col_hi);
+    c->k = k2;
+    const long long need = (long long)n_new + 2LL * m.halo_cap;
+    if (need > m.capacity) m.capacity = (int)(n_new + n_new / 4 + 4ULL * m.halo_cap + 1024ULL);
+    ParticleSet &f = c->fluid;
+    const float mass_value = f.uniform_mass_value;
+    free_set_public(f);
+    rc = alloc_set(f, m.capacity, c->k.ncells, false, false);
+    if (rc) return rc;
+    f.n = m.capacity;
+    f.d_n_cur = m.d_counts;
+    f.d_n_in = m.d_counts + 1;
+    f.windowed = true;
+    f.uniform_mass = true;
+    f.uniform_mass_value = mass_value;
+    const int counts[2] = {(int)n_new, (int)n_new};
+    SPHB_CUDA(cudaMemcpyAsync(m.d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_unpack_moved(c->stream, f, d.recv, (int)n_new);
+    m.n_uploaded = (int)n_new;
+    if (m.bnd_n_global > 0) {
+        ParticleSet &b = c->boundary;
+        b.pc ^= 1; b.vc ^= 1; b.ic ^= 1; b.mc ^= 1; b.xc ^= 1;      // back to the buffers that hold the whole tank's walls
+        rc = mg_window_boundary(c);
+        if (rc) return rc;
+    }
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    if (changed_out) *changed_out = 1;
+    return SPHB_OK;
+}
+
+}  // namespace
 }  // namespace sphb
 
 using namespace sphb;
@@ -693,6 +920,24 @@ int sphb_mg_allreduce_stats(sphb_ctx *c, sphb_stats *inout)
     inout->max_cell_count = (unsigned int)h[11]; inout->n_boundary = (unsigned int)h[12];
     inout->last_rho_err_ref = 0.0f;
     return SPHB_OK;
+}
+
+int sphb_mg_rebalance(sphb_ctx *c, int min_width, double column_cost, double min_imbalance, int *changed_out)
+{
+    SPHB_ENTER(c);
+    Exchange x;
+    x.nccl = true;
+    return rebalance_impl(c, min_width, column_cost, min_imbalance, x, changed_out);
+}
+
+int sphb_mg_rebalance_host(sphb_ctx *c, int min_width, double column_cost, double min_imbalance,
+                           sphb_mg_allreduce_u64_fn allreduce, sphb_mg_alltoallv_fn alltoallv, void *user, int *changed_out)
+{
+    SPHB_ENTER(c);
+    if (!allreduce || !alltoallv) { set_error("sphb_mg_rebalance_host: both callbacks are needed"); return SPHB_E_ARG; }
+    Exchange x;
+    x.nccl = false; x.ar = allreduce; x.a2a = alltoallv; x.user = user;
+    return rebalance_impl(c, min_width, column_cost, min_imbalance, x, changed_out);
 }
 
 int sphb_mg_info(sphb_ctx *c, sphb_mg_info_t *out)

@@ -9,6 +9,9 @@ owned particles and compares them BIT FOR BIT with a single-GPU run of the same 
 "ipc1dev": the same peer-store transport with every rank on CUDA device 0 — N processes sharing ONE GPU,
 receive blocks mapped across processes with cudaIpc*, handles carried by gloo, no NCCL anywhere — so the
 cross-process transport is testable on a one-GPU box.
+A second argument `recut=K` re-cuts the running slabs every K steps (sphb_mg_rebalance over NCCL, or — "ipc1dev" —
+sphb_mg_rebalance_host with the bytes carried by gloo): the run must stay bit-identical to the single GPU and the
+spread of the ranks' particle counts must shrink.
 Prints "mg_nccl_check ok" / "mg_ipc_check ok" / "mg_ipc1dev_check ok"."""
 import os
 import sys
@@ -25,6 +28,7 @@ import pi_sph_fluid_b200 as pkg  # noqa: E402
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     transport = sys.argv[1] if len(sys.argv) > 1 else "nccl"
+    recut = int(sys.argv[2].split("=")[1]) if len(sys.argv) > 2 and sys.argv[2].startswith("recut=") else 0
     one_dev = transport == "ipc1dev"
     dev = 0 if one_dev else int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(dev)
@@ -54,7 +58,28 @@ def main():
     slab.upload(part, boundary, id_base=base)
     slab.init_boundary()
     slab.compute_accel(*g)
-    slab.step(steps, *g)
+    spread = []
+    if recut:
+        def counts():
+            per = [None] * world
+            dist.all_gather_object(per, slab.stats()["n_fluid"])
+            return per
+        done, n_recuts = 0, 0
+        while done < steps:
+            k = min(recut, steps - done)
+            slab.step(k, *g)
+            done += k
+            if done < steps:
+                before = counts()
+                changed = slab.rebalance_host(dist) if one_dev else slab.rebalance()
+                after = counts()
+                n_recuts += int(changed)
+                spread.append((max(before) - min(before), max(after) - min(after), changed))
+                assert sum(after) == sum(before)
+        if rank == 0:
+            print(f"re-cuts: {n_recuts} of {len(spread)} calls moved the cuts; (max-min) owned before -> after: {spread}")
+    else:
+        slab.step(steps, *g)
     ids, f, du, dv = slab.download()
     if one_dev:
         per = [None] * world
@@ -83,14 +108,22 @@ def main():
             out[i] = ff; odu[i] = a; odv[i] = b; seen[i] += 1
             migrated += int(((i < base_r) | (i >= base_r + n_r)).sum())      # owned now, uploaded elsewhere
         ok = bool((seen == 1).all())
+        if not ok:
+            print(f"ownership: {int((seen == 0).sum())} particles owned by nobody, {int((seen > 1).sum())} by several ranks")
         for fld in out.dtype.names:
-            ok &= bool(np.array_equal(out[fld].view("u4"), rf[fld].view("u4")))
+            same = out[fld].view("u4") == rf[fld].view("u4")
+            if not same.all():
+                print(f"field {fld}: {int((~same).sum())} of {len(same)} particles differ, first ids {np.nonzero(~same)[0][:8]}")
+            ok &= bool(same.all())
         ok &= bool(np.array_equal(odu.view("u4"), rdu.view("u4")) and np.array_equal(odv.view("u4"), rdv.view("u4")))
         ok &= st["n_fluid"] == len(full) and st["n_lost"] == 0 and st["n_overflow"] == 0
         ok &= abs(st["kinetic"] - rst["kinetic"]) <= 1e-9 * abs(rst["kinetic"]) and st["max_speed"] == rst["max_speed"]
         moved = sum(int(((pkg.columns_of(prm, ff["x"]) < cuts[r]) | (pkg.columns_of(prm, ff["x"]) >= cuts[r + 1])).sum())
                     for r, (i, ff, a, b, _b, _n) in enumerate(gathered))
-        ok &= migrated > 0 or world == 1
+        # (with re-cuts the cuts may follow the flow so well that every particle stays with its first owner)
+        ok &= migrated > 0 or world == 1 or recut > 0
+        if recut:
+            ok &= any(sp[2] for sp in spread)          # at least one call moved the cuts
         print(f"world {world} ({transport}): {len(full)} particles, {steps} steps, migrated {migrated}, owned-out-of-slab {moved}, "
               f"message {info['message_bytes']} B, sent {info['bytes_sent']} B, identical={ok}")
     flag = torch.tensor([1 if ok else 0]) if one_dev else torch.tensor([1 if ok else 0], device=f"cuda:{dev}")

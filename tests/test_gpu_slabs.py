@@ -205,6 +205,19 @@ def test_cross_process_peer_store_transport_on_one_device(lib_built, world):
     assert "mg_ipc1dev_check ok" in r.stdout
 
 
+def test_cross_process_recut_on_one_device(lib_built):
+    """sphb_mg_rebalance_host across three processes (device 0, peer-store halo transport, bytes of the re-cut
+    carried by gloo): a dam break under a strong sideways pull is re-cut every 40 steps — bit-identical to the
+    single-GPU run, and every re-cut that moves the cuts narrows the spread of the ranks' particle counts."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3",
+                        "--master-addr", "127.0.0.1", "--master-port", "29647",
+                        str(ROOT / "tests" / "mg_nccl_check.py"), "ipc1dev", "recut=40"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mg_ipc1dev_check ok" in r.stdout and "re-cuts:" in r.stdout
+
+
 def test_ipc_transport_single_process_loopback(lib_built):
     """World 1 has no neighbour: connecting the peer-store transport needs no handle and the slab
     steps like a single-GPU run; a handle without a neighbour is refused."""

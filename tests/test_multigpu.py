@@ -31,3 +31,19 @@ def test_process_per_gpu_transports_under_torchrun(lib_built, world, transport):
     assert f"mg_{transport}_check ok" in r.stdout
 
 
+
+
+@pytest.mark.parametrize("world", [2])
+def test_recut_over_nccl_under_torchrun(lib_built, world):
+    """sphb_mg_rebalance (ncclAllReduce of the column counts, ncclSend/ncclRecv of the particles) every 100 steps of
+    a dam break that drains to the right: bit-identical to the single GPU, spread of the ranks' counts shrinks."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29635",
+                        str(ROOT / "tests" / "mg_nccl_check.py"), "ipc", "recut=100"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mg_ipc_check ok" in r.stdout and "re-cuts:" in r.stdout
