@@ -47,3 +47,22 @@ def test_recut_over_nccl_under_torchrun(lib_built, world):
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "mg_ipc_check ok" in r.stdout and "re-cuts:" in r.stdout
+
+
+@pytest.mark.parametrize("workload,steps", [("dam64m", 5), ("slosh16m", 20)])
+def test_full_size_configs_bit_identical_to_one_gpu(lib_built, workload, steps):
+    """BASELINE configs[3] (64M dam break) and configs[4] (16M sloshing tank, tilt trace) on every visible GPU
+    (8 on the bench box) against ONE GPU at the same size: per-field 64-bit hashes of x, y, u, v, m, rho, p,
+    du_dt, dv_dt equal, plus an oracle spot check of a strip straddling a cut (tests/mg_full_check.py; the
+    8-GPU log is committed as profiles/r02_mg_full_check_8gpu.log)."""
+    import torch
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29637",
+                        str(ROOT / "tests" / "mg_full_check.py"), workload, str(steps)],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mg_full_check ok" in r.stdout and "EQUAL" in r.stdout and "bit-for-bit" in r.stdout
