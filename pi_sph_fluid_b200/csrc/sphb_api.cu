@@ -367,21 +367,34 @@ int sphb_upload(sphb_ctx *c, const sphb_particle *fluid, int n_fluid, const sphb
     const size_t fb = (size_t)n_fluid * sizeof(sphb_particle), bb = (size_t)n_boundary * sizeof(sphb_particle);
     int rc = ensure_stage(c, (fb > bb ? fb : bb) + 16);
     if (rc) return rc;
-    // the copy is on its way while the host looks at the masses
     if (n_fluid > 0) SPHB_CUDA(cudaMemcpyAsync(c->d_stage, fluid, fb, cudaMemcpyHostToDevice, c->stream));
-    // uniform fluid mass (the reference sets every m = RHO_0*V, :502) selects the kernels
-    // that keep the mass in the constant bank
+    // uniform fluid mass (the reference sets every m = RHO_0*V, :502) selects the kernels that keep the
+    // mass in the constant bank; the conversion kernel itself reports whether the masses differ
     bool uniform = true;
-    for (int i = 1; i < n_fluid && uniform; i++) uniform = (memcmp(&fluid[i].m, &fluid[0].m, sizeof(float)) == 0);
-    rc = alloc_set(c->fluid, n_fluid, c->k.ncells, false, !uniform);
+    rc = alloc_set(c->fluid, n_fluid, c->k.ncells, false, c->fluid.mass[0] != nullptr);
     if (rc) return rc;
+    if (n_fluid > 0) {
+        uint32_t m0_bits;
+        memcpy(&m0_bits, &fluid[0].m, sizeof m0_bits);
+        unsigned int *d_differs = &c->d_counters[1].list_flushes;      // scratch word of the boundary's counter block
+        unsigned int differs = 0;
+        SPHB_CUDA(cudaMemsetAsync(d_differs, 0, sizeof(unsigned int), c->stream));
+        c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(c->d_stage), c->fluid, false, -1,
+                                         nullptr, 0, m0_bits, d_differs);
+        SPHB_CUDA(cudaMemcpyAsync(&differs, d_differs, sizeof differs, cudaMemcpyDeviceToHost, c->stream));
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));     // d_stage is reused below
+        uniform = differs == 0;
+        if (!uniform && c->fluid.mass[0] == nullptr) {
+            // first set with per-particle masses: the arrays that carry them, and the conversion again
+            rc = alloc_set(c->fluid, n_fluid, c->k.ncells, false, true);
+            if (rc) return rc;
+            c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(c->d_stage), c->fluid, false);
+            SPHB_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
     c->fluid.uniform_mass = uniform;
     c->fluid.uniform_mass_value = n_fluid > 0 ? fluid[0].m : c->prm.rho0 * c->prm.vol;
     c->k.mass = c->fluid.uniform_mass_value;
-    if (n_fluid > 0) {
-        c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(c->d_stage), c->fluid, false);
-        SPHB_CUDA(cudaStreamSynchronize(c->stream));     // d_stage is reused below
-    }
     if (n_boundary > 0) {
         rc = alloc_set(c->boundary, n_boundary, c->k.ncells, true, true);
         if (rc) return rc;

@@ -358,7 +358,8 @@ int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const Sla
 int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc, DeviceCounters *ctr);
 int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deterministic);
 int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, bool is_boundary, int n = -1,
-                      const uint32_t *ids = nullptr, uint32_t id_base = 0);
+                      const uint32_t *ids = nullptr, uint32_t id_base = 0, uint32_t m0_bits = 0,
+                      unsigned int *mass_differs = nullptr);
 int launch_pack_owned(cudaStream_t st, const Consts &k, const ParticleSet &ps, int cap, sphb_particle *aos,
                       uint32_t *ids_out, float *du, float *dv, unsigned int *n_out);
 int launch_soa_to_aos(cudaStream_t st, const ParticleSet &ps, sphb_particle *aos, float *du, float *dv, bool is_boundary);

@@ -517,8 +517,8 @@ int sphb_mg_configure(sphb_ctx *c, int rank, int world, int col_lo, int col_hi, 
     }
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_send_cnt), 2 * sizeof(uint32_t)));
     SPHB_CUDA(cudaMemset(m.d_send_cnt, 0, 2 * sizeof(uint32_t)));
-    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_flags), 2 * sizeof(unsigned int)));
-    SPHB_CUDA(cudaMemset(m.d_flags, 0, 2 * sizeof(unsigned int)));
+    SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_flags), 4 * sizeof(unsigned int)));      // [2]: scratch of the upload
+    SPHB_CUDA(cudaMemset(m.d_flags, 0, 4 * sizeof(unsigned int)));
     SPHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m.d_counts), 4 * sizeof(int)));
     SPHB_CUDA(cudaMemset(m.d_counts, 0, 4 * sizeof(int)));
     SPHB_CUDA(cudaEventCreateWithFlags(&m.ev_sent, cudaEventDisableTiming));
@@ -679,15 +679,21 @@ int sphb_mg_upload(sphb_ctx *c, const sphb_particle *fluid, const uint32_t *ids,
         uint32_t *d_ids = ids ? reinterpret_cast<uint32_t *>(base + ((fb + 15) & ~(size_t)15)) : nullptr;
         SPHB_CUDA(cudaMemcpyAsync(base, fluid, fb, cudaMemcpyHostToDevice, c->stream));
         if (ids) SPHB_CUDA(cudaMemcpyAsync(d_ids, ids, ib, cudaMemcpyHostToDevice, c->stream));
-        // while the copies are on their way the host checks the masses
-        for (int i = 1; i < n_fluid; i++)
-            if (memcmp(&fluid[i].m, &fluid[0].m, sizeof(float)) != 0) {
-                cudaStreamSynchronize(c->stream);
-                f.n = 0;
-                set_error("slab contexts need a uniform fluid mass (the reference's m = RHO_0*V, :502)");
-                return SPHB_E_ARG;
-            }
-        c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(base), f, false, n_fluid, d_ids, id_base);
+        // slabs need the reference's uniform fluid mass (:502): the conversion kernel checks it on the fly
+        uint32_t m0_bits;
+        memcpy(&m0_bits, &fluid[0].m, sizeof m0_bits);
+        unsigned int *d_differs = m.d_flags + 2;
+        unsigned int differs = 0;
+        SPHB_CUDA(cudaMemsetAsync(d_differs, 0, sizeof(unsigned int), c->stream));
+        c->launches += launch_aos_to_soa(c->stream, reinterpret_cast<const sphb_particle *>(base), f, false, n_fluid, d_ids, id_base,
+                                         m0_bits, d_differs);
+        SPHB_CUDA(cudaMemcpyAsync(&differs, d_differs, sizeof differs, cudaMemcpyDeviceToHost, c->stream));
+        SPHB_CUDA(cudaStreamSynchronize(c->stream));
+        if (differs) {
+            f.n = 0;
+            set_error("slab contexts need a uniform fluid mass (the reference's m = RHO_0*V, :502)");
+            return SPHB_E_ARG;
+        }
     } else {
         f.pc = f.vc = f.ic = f.mc = f.xc = 0;
         f.sorted = false;
