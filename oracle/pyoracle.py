@@ -58,6 +58,13 @@ def build(ref: bool = True) -> None:
                    stdout=subprocess.DEVNULL)
 
 
+def build_refmain() -> Path:
+    """oracle/_ref/pi_sph_fluid_main_b200: the reference's own main() linked against libsphb200.so (oracle/Makefile
+    `refmain`; needs the library built and, to (re)build, /root/reference).  Returns the binary's path."""
+    subprocess.run(["make", "-C", str(HERE), "refmain"], check=True, stdout=subprocess.DEVNULL)
+    return HERE / "_ref" / "pi_sph_fluid_main_b200"
+
+
 def cpu_level() -> str:
     """'v4' if the host CPU can run the AVX-512 builds, else 'v3'."""
     try:
