@@ -349,6 +349,8 @@ void draw_metaballs(unsigned char *draw_buffer, struct particle *pixel_pseudopar
  * (default: sphb_default_params(0.075, 4, 2), H re-derived as cell_length/2 per context). */
 int sphb_compat_set_params(const sphb_params *prm);
 void sphb_compat_free_context(struct neighbors_context *ctx);
+/* releases the private context calculate_particle_pressure keeps (its signature carries none); also done at exit */
+void sphb_compat_shutdown(void);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus

@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
         "sphb_build_info": (C.c_char_p, []),
         "sphb_compat_set_params": (ci, [vp]),
         "sphb_compat_free_context": (None, [vp]),
+        "sphb_compat_shutdown": (None, []),
         "alloc_neighbors_context": (vp, [ci, cf, cf, cf, cf, cf]),
         "update_neighbors_context": (None, [vp, vp]),
         "calculate_boundary_pseudomass": (None, [vp, vp]),

@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "sphb_internal.cuh"
 #include "sph_consts.h"
 
@@ -27,6 +29,7 @@ struct neighbors_context {
     int n_particles;
     bool built;
     sphb_particle *h_tmp;  // host bounce buffer for partial write-back
+    float2 *h_pixels;      // draw_metaballs: the pixel centres uploaded last (the reference builds them once, :570-577)
 };
 
 namespace {
@@ -71,6 +74,24 @@ unsigned int refresh(neighbors_context *ctx, const sphb_particle *aos, const cha
     return moved;
 }
 
+struct PressureScratch {
+    std::mutex mu;
+    sphb_ctx *ctx = nullptr;
+    sphb_particle *h_tmp = nullptr;
+    int h_cap = 0;
+    bool at_exit = false;
+} g_pressure;
+
+void pressure_release()
+{
+    std::lock_guard<std::mutex> lock(g_pressure.mu);
+    if (g_pressure.ctx) sphb_destroy(g_pressure.ctx);
+    free(g_pressure.h_tmp);
+    g_pressure.ctx = nullptr;
+    g_pressure.h_tmp = nullptr;
+    g_pressure.h_cap = 0;
+}
+
 void require_built(neighbors_context *ctx, const char *where)
 {
     if (!ctx || !ctx->core || !ctx->built) {
@@ -82,6 +103,8 @@ void require_built(neighbors_context *ctx, const char *where)
 }  // namespace
 
 extern "C" {
+
+void sphb_compat_shutdown(void) { pressure_release(); }
 
 int sphb_compat_set_params(const sphb_params *prm)
 {
@@ -118,6 +141,7 @@ void sphb_compat_free_context(struct neighbors_context *ctx)
     if (!ctx) return;
     sphb_destroy(ctx->core);
     free(ctx->h_tmp);
+    free(ctx->h_pixels);
     free(ctx);
 }
 
@@ -189,11 +213,17 @@ void calculate_density(struct particle *fluid, struct particle *boundary, struct
 void calculate_particle_pressure(struct particle *particles, int n_particles)
 {
     const char *where = "calculate_particle_pressure";
-    static sphb_ctx *scratch = nullptr;
-    static sphb_particle *h_tmp = nullptr;
-    static int h_cap = 0;
     if (n_particles <= 0) return;
-    if (!scratch && sphb_create(&compat_params(), &scratch)) die(where);
+    // the signature carries no context: one private context for the process, serialised (the reference calls
+    // this from every thread of its OpenMP team, :631) and released by sphb_compat_shutdown / at exit
+    std::lock_guard<std::mutex> lock(g_pressure.mu);
+    sphb_ctx *&scratch = g_pressure.ctx;
+    sphb_particle *&h_tmp = g_pressure.h_tmp;
+    int &h_cap = g_pressure.h_cap;
+    if (!scratch) {
+        if (sphb_create(&compat_params(), &scratch)) die(where);
+        if (!g_pressure.at_exit) { atexit(pressure_release); g_pressure.at_exit = true; }
+    }
     sphb_ctx *c = scratch;
     sphb_particle *p = reinterpret_cast<sphb_particle *>(particles);
     COMPAT_CUDA(cudaSetDevice(c->device), where);
@@ -249,10 +279,19 @@ void draw_metaballs(unsigned char *draw_buffer, struct particle *pixel_pseudopar
         COMPAT_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_pixels), sizeof(float2) * 64 * 128), where);
         COMPAT_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_frame), 1024), where);
     }
-    float2 *h = static_cast<float2 *>(malloc(sizeof(float2) * 64 * 128));
-    for (int i = 0; i < 64 * 128; i++) h[i] = make_float2(px[i].x, px[i].y);
-    COMPAT_CUDA(cudaMemcpy(c->d_pixels, h, sizeof(float2) * 64 * 128, cudaMemcpyHostToDevice), where);
-    free(h);
+    // the pixel centres travel to HBM only when they differ from the ones uploaded last (the reference builds
+    // them once, :570-577, and hands the same array to every frame)
+    bool fresh = ctx_fluid->h_pixels == nullptr;
+    if (fresh) {
+        ctx_fluid->h_pixels = static_cast<float2 *>(malloc(sizeof(float2) * 64 * 128));
+        if (!ctx_fluid->h_pixels) { set_error("out of memory"); die(where); }
+    }
+    for (int i = 0; i < 64 * 128; i++) {
+        const float2 v = make_float2(px[i].x, px[i].y);
+        if (fresh || memcmp(&v, &ctx_fluid->h_pixels[i], sizeof v) != 0) { ctx_fluid->h_pixels[i] = v; fresh = true; }
+    }
+    if (fresh)
+        COMPAT_CUDA(cudaMemcpyAsync(c->d_pixels, ctx_fluid->h_pixels, sizeof(float2) * 64 * 128, cudaMemcpyHostToDevice, c->stream), where);
     const float px_width = c->prm.width / 128;                  // :399
     const float W_px = host_W(c->prm.H, px_width / 2);           // :401
     c->launches += launch_render(c->stream, c->k, c->fluid, c->d_pixels, W_px, c->d_frame);

@@ -19,6 +19,7 @@ def _declared_functions():
         text = (ROOT / "include" / h).read_text()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+        text = re.sub(r"\btypedef\s+\w+\s*\(\s*\*[^;]*;", "", text)      # function-pointer typedefs declare no symbol
         names += re.findall(r"\b([a-z_][a-z0-9_]*)\s*\([^;{}]*\)\s*;", text)
     return sorted(set(names))
 
