@@ -318,6 +318,16 @@ int sphb_mg_rebalance(sphb_ctx *ctx, int min_width, double column_cost, double m
 int sphb_mg_rebalance_host(sphb_ctx *ctx, int min_width, double column_cost, double min_imbalance,
                            sphb_mg_allreduce_u64_fn allreduce, sphb_mg_alltoallv_fn alltoallv, void *user, int *changed_out);
 
+/* State files of a slab run: every rank writes ONE part (its owned particles with their global ids, du_dt/dv_dt,
+ * the parameters, the step count, and the whole tank's boundary).  sphb_mg_load_state gives a freshly
+ * configured slab context (sphb_create + sphb_mg_configure, any rank count, any cuts) the particles of ALL the
+ * parts that fall into its columns, restores their accelerations and the boundary; after sphb_init_boundary the
+ * run continues bit-identically — on a different number of ranks if wanted (1 rank: one slab over all columns).
+ * Layout: 64-byte header (version 2) | sphb_params | ids[n] | struct particle[n] | du_dt[n] | dv_dt[n] |
+ * struct particle boundary[nb]; oracle/pyoracle.py load_state reads both versions. */
+int sphb_mg_save_state(sphb_ctx *ctx, const char *path);
+int sphb_mg_load_state(sphb_ctx *ctx, const char *const *paths, int n_paths);
+
 int sphb_mg_group_compute_accel(sphb_ctx **ctxs, int n, float gravity_x, float gravity_y);
 /* gravity_xy: NULL (constant gravity_x/y) or nsteps (gx, gy) pairs */
 int sphb_mg_group_step(sphb_ctx **ctxs, int n, float gravity_x, float gravity_y, const float *gravity_xy, int nsteps);

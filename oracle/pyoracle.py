@@ -65,6 +65,42 @@ def build_refmain() -> Path:
     return HERE / "_ref" / "pi_sph_fluid_main_b200"
 
 
+def load_state(paths):
+    """Reader of libsphb200's state files for the oracle side: one version-1 file (sphb_save_state) or the
+    version-2 parts of a slab run (sphb_mg_save_state, any number of ranks).  -> dict(R, H, steps, fluid, du, dv,
+    boundary) with the fluid in ORIGINAL particle order, ready for Oracle.step."""
+    if isinstance(paths, (str, Path)):
+        paths = [paths]
+    parts, out = [], {}
+    for p in paths:
+        raw = Path(p).read_bytes()
+        assert raw[:8] == b"SPHB200\0", f"{p}: not a libsphb200 state file"
+        version, params_bytes, n, nb = np.frombuffer(raw, "<u4", 4, 8)
+        steps = int(np.frombuffer(raw, "<u8", 1, 24)[0])
+        prm = np.frombuffer(raw, "<f4", 14, 64)             # R, H, width, height, rho0, c0, g, dt, vol, x/y min/max, cell
+        off = 64 + int(params_bytes)
+        ids = np.arange(n, dtype=np.uint32)
+        if version == 2:
+            ids = np.frombuffer(raw, "<u4", n, off); off += 4 * n
+        else:
+            assert version == 1, f"{p}: unknown version {version}"
+        fluid = np.frombuffer(raw, PARTICLE, n, off); off += 28 * n
+        du = np.frombuffer(raw, "<f4", n, off); off += 4 * n
+        dv = np.frombuffer(raw, "<f4", n, off); off += 4 * n
+        if not out:
+            out = dict(R=float(prm[0]), H=float(prm[1]), steps=steps, boundary=np.frombuffer(raw, PARTICLE, nb, off).copy())
+        assert steps == out["steps"], "parts from different steps"
+        parts.append((ids, fluid, du, dv))
+    total = sum(len(i) for i, _, _, _ in parts)
+    out["fluid"] = np.zeros(total, PARTICLE); out["du"] = np.zeros(total, np.float32); out["dv"] = np.zeros(total, np.float32)
+    seen = np.zeros(total, bool)
+    for ids, f, du, dv in parts:
+        assert not seen[ids].any(), "a particle appears in two parts"
+        out["fluid"][ids] = f; out["du"][ids] = du; out["dv"][ids] = dv; seen[ids] = True
+    assert seen.all()
+    return out
+
+
 def cpu_level() -> str:
     """'v4' if the host CPU can run the AVX-512 builds, else 'v3'."""
     try:

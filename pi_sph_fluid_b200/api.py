@@ -147,6 +147,8 @@ def lib() -> C.CDLL:
         "sphb_mg_merge_stats": (ci, [vp, ci, vp]),
         "sphb_mg_allreduce_stats": (ci, [vp, vp]),
         "sphb_mg_info": (ci, [vp, vp]),
+        "sphb_mg_save_state": (ci, [vp, C.c_char_p]),
+        "sphb_mg_load_state": (ci, [vp, vp, ci]),
         "sphb_mg_rebalance": (ci, [vp, ci, C.c_double, C.c_double, vp]),
         "sphb_mg_rebalance_host": (ci, [vp, ci, C.c_double, C.c_double, vp, vp, vp, vp]),
     }
@@ -542,6 +544,16 @@ class Slab(Simulation):
                "sphb_mg_download")
         return n.value
 
+    def save_state(self, path):
+        """sphb_mg_save_state: this rank's part of a slab run's state file."""
+        _check(lib().sphb_mg_save_state(self._h, str(path).encode()), "sphb_mg_save_state")
+
+    def load_parts(self, paths):
+        """sphb_mg_load_state: the particles of ALL parts that fall into this (configured) rank's columns."""
+        arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+        _check(lib().sphb_mg_load_state(self._h, arr, len(paths)), "sphb_mg_load_state")
+        self.n_boundary = 1      # the parts carry the boundary: sphb_init_boundary has work to do
+
     def rebalance(self, min_width: int = 4, column_cost: float = 0.0, min_imbalance: float = 0.0) -> bool:
         """sphb_mg_rebalance (collective, NCCL): re-cut the running slabs at the current quantiles; True if the cuts moved."""
         changed = C.c_int(0)
@@ -657,6 +669,19 @@ class SlabGroup:
         self.upload(fluid, boundary, accel=(du, dv))
         self.init_boundary()
         return self.cuts
+
+    def save_state(self, prefix) -> list:
+        """One part file per slab (sphb_mg_save_state); returns their paths."""
+        paths = [f"{prefix}.part{r}" for r in range(len(self.slabs))]
+        for s, p in zip(self.slabs, paths):
+            s.save_state(p)
+        return paths
+
+    def load_parts(self, paths):
+        """Every slab takes the particles of ALL parts that fall into its columns (any rank count wrote them)."""
+        for s in self.slabs:
+            s.load_parts(paths)
+        self.n_fluid = sum(int(s.stats()["n_fluid"]) for s in self.slabs)
 
     def init_boundary(self):
         for s in self.slabs:

@@ -928,6 +928,142 @@ int sphb_mg_allreduce_stats(sphb_ctx *c, sphb_stats *inout)
     return SPHB_OK;
 }
 
+// ---- state files of a slab run ---------------------------------------------------------------
+// One PART file per rank: 64-byte header (version 2: rank, world, owned columns) | sphb_params | global ids[n] |
+// struct particle fluid[n] | du_dt[n] | dv_dt[n] | the whole tank's boundary[nb] (every part carries it: it is
+// small and makes each part self-describing).  sphb_mg_load_state gives a freshly configured slab context the
+// particles of ALL parts that fall into ITS columns — so a run saved on N ranks continues on M ranks (M = 1:
+// one slab over all columns), bit-identically.
+struct PartHeader {
+    char magic[8];                  // "SPHB200\0"
+    uint32_t version, params_bytes;
+    uint32_t n_fluid, n_boundary;
+    unsigned long long steps;
+    uint32_t has_accel, rank, world, col_lo, col_hi, reserved[3];
+};
+static_assert(sizeof(PartHeader) == 64, "header layout");
+
+int sphb_mg_save_state(sphb_ctx *c, const char *path)
+{
+    SPHB_ENTER(c);
+    MgState &m = c->mg;
+    if (!path) return SPHB_E_ARG;
+    if (!m.on) { set_error("not a slab context (single GPU: sphb_save_state)"); return SPHB_E_STATE; }
+    if (!c->fluid.sorted) { set_error("no sorted state yet (sphb_compute_accel first)"); return SPHB_E_STATE; }
+    int n_cur = 0;
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaMemcpy(&n_cur, m.d_counts, sizeof n_cur, cudaMemcpyDeviceToHost));
+    const int cap = n_cur > 0 ? n_cur : 1, nb = m.bnd_n_global;
+    sphb_particle *f = static_cast<sphb_particle *>(malloc(sizeof(sphb_particle) * (size_t)cap));
+    uint32_t *ids = static_cast<uint32_t *>(malloc(4 * (size_t)cap));
+    float *du = static_cast<float *>(malloc(4 * (size_t)cap)), *dv = static_cast<float *>(malloc(4 * (size_t)cap));
+    sphb_particle *b = static_cast<sphb_particle *>(malloc(sizeof(sphb_particle) * (size_t)(nb > 0 ? nb : 1)));
+    int rc = (f && ids && du && dv && b) ? SPHB_OK : SPHB_E_NOMEM, n = 0;
+    if (!rc) rc = sphb_mg_download(c, cap, f, ids, du, dv, &n);
+    if (!rc && nb > 0) {
+        // the whole tank's walls live in the buffers the windowed sort read from (mg_window_boundary)
+        ParticleSet g = c->boundary;
+        g.pc ^= 1; g.vc ^= 1; g.ic ^= 1; g.mc ^= 1; g.xc ^= 1;
+        g.n = nb;
+        rc = ensure_stage(c, (size_t)nb * sizeof(sphb_particle) + 64);
+        if (!rc) {
+            c->launches += launch_soa_to_aos(c->stream, g, static_cast<sphb_particle *>(c->d_stage), nullptr, nullptr, true);
+            cudaError_t e = cudaMemcpyAsync(b, c->d_stage, (size_t)nb * sizeof(sphb_particle), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "boundary download", __FILE__, __LINE__);
+        }
+    }
+    if (!rc) {
+        PartHeader h;
+        memset(&h, 0, sizeof h);
+        memcpy(h.magic, "SPHB200", 8);
+        h.version = 2; h.params_bytes = (uint32_t)sizeof(sphb_params);
+        h.n_fluid = (uint32_t)n; h.n_boundary = (uint32_t)nb; h.steps = c->steps; h.has_accel = c->accel_ready ? 1u : 0u;
+        h.rank = (uint32_t)m.rank; h.world = (uint32_t)m.world; h.col_lo = (uint32_t)m.col_lo; h.col_hi = (uint32_t)m.col_hi;
+        FILE *fp = fopen(path, "wb");
+        bool ok = fp != nullptr;
+        ok = ok && fwrite(&h, sizeof h, 1, fp) == 1 && fwrite(&c->prm, sizeof c->prm, 1, fp) == 1;
+        ok = ok && (n == 0 || (fwrite(ids, 4, n, fp) == (size_t)n && fwrite(f, sizeof *f, n, fp) == (size_t)n &&
+                               fwrite(du, 4, n, fp) == (size_t)n && fwrite(dv, 4, n, fp) == (size_t)n));
+        ok = ok && (nb == 0 || fwrite(b, sizeof *b, nb, fp) == (size_t)nb);
+        if (fp) ok = (fclose(fp) == 0) && ok;
+        if (!ok) { set_error("cannot write state file %s", path); rc = SPHB_E_ARG; }
+    }
+    free(f); free(ids); free(du); free(dv); free(b);
+    return rc;
+}
+
+int sphb_mg_load_state(sphb_ctx *c, const char *const *paths, int n_paths)
+{
+    SPHB_ENTER(c);
+    MgState &m = c->mg;
+    if (!paths || n_paths < 1) return SPHB_E_ARG;
+    if (!m.on) { set_error("sphb_mg_configure the context first (its columns decide which particles it takes)"); return SPHB_E_STATE; }
+    sphb_particle *f = nullptr, *b = nullptr;
+    uint32_t *ids = nullptr;
+    float *du = nullptr, *dv = nullptr;
+    size_t n = 0, cap = 0, nb = 0;
+    unsigned long long steps = 0;
+    bool has_accel = true;
+    int rc = SPHB_OK;
+    for (int p = 0; p < n_paths && !rc; p++) {
+        FILE *fp = fopen(paths[p], "rb");
+        if (!fp) { set_error("cannot open state file %s", paths[p]); rc = SPHB_E_ARG; break; }
+        PartHeader h;
+        sphb_params prm;
+        if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "SPHB200", 8) != 0 || h.version != 2 ||
+            h.params_bytes != sizeof(sphb_params) || fread(&prm, sizeof prm, 1, fp) != 1) {
+            set_error("%s is not a version-2 (slab part) state file", paths[p]);
+            rc = SPHB_E_ARG;
+        } else if (prm.R != c->prm.R || prm.H != c->prm.H || prm.cell_length != c->prm.cell_length || prm.x_min != c->prm.x_min ||
+                   prm.x_max != c->prm.x_max || prm.y_min != c->prm.y_min || prm.y_max != c->prm.y_max) {
+            set_error("%s was written for another scene (R, H or the tank differ from this context's parameters)", paths[p]);
+            rc = SPHB_E_ARG;
+        }
+        if (!rc) {
+            if (p == 0) steps = h.steps;
+            else if (h.steps != steps) { set_error("%s is from step %llu, the first part from step %llu", paths[p], h.steps, steps); rc = SPHB_E_ARG; }
+            has_accel = has_accel && h.has_accel != 0;
+        }
+        const size_t np_ = h.n_fluid;
+        uint32_t *pid = nullptr; sphb_particle *pf = nullptr; float *pdu = nullptr, *pdv = nullptr;
+        if (!rc && np_ > 0) {
+            pid = static_cast<uint32_t *>(malloc(4 * np_)); pf = static_cast<sphb_particle *>(malloc(sizeof(sphb_particle) * np_));
+            pdu = static_cast<float *>(malloc(4 * np_)); pdv = static_cast<float *>(malloc(4 * np_));
+            if (!pid || !pf || !pdu || !pdv) rc = SPHB_E_NOMEM;
+            else if (fread(pid, 4, np_, fp) != np_ || fread(pf, sizeof *pf, np_, fp) != np_ || fread(pdu, 4, np_, fp) != np_ ||
+                     fread(pdv, 4, np_, fp) != np_) { set_error("%s is truncated", paths[p]); rc = SPHB_E_ARG; }
+        }
+        if (!rc && p == 0 && h.n_boundary > 0) {
+            nb = h.n_boundary;
+            b = static_cast<sphb_particle *>(malloc(sizeof(sphb_particle) * nb));
+            if (!b) rc = SPHB_E_NOMEM;
+            else if (fread(b, sizeof *b, nb, fp) != nb) { set_error("%s is truncated", paths[p]); rc = SPHB_E_ARG; }
+        }
+        fclose(fp);
+        // keep what falls into this rank's columns (:112 decides the column, as everywhere)
+        for (size_t i = 0; i < np_ && !rc; i++) {
+            const int col = sphb_column_of(&c->prm, pf[i].x);
+            if (col < m.col_lo || col >= m.col_hi) continue;
+            if (n == cap) {
+                cap = cap ? cap * 2 : (np_ > 1024 ? np_ : 1024);
+                f = static_cast<sphb_particle *>(realloc(f, sizeof(sphb_particle) * cap)); ids = static_cast<uint32_t *>(realloc(ids, 4 * cap));
+                du = static_cast<float *>(realloc(du, 4 * cap)); dv = static_cast<float *>(realloc(dv, 4 * cap));
+                if (!f || !ids || !du || !dv) { rc = SPHB_E_NOMEM; break; }
+            }
+            f[n] = pf[i]; ids[n] = pid[i]; du[n] = pdu[i]; dv[n] = pdv[i];
+            n++;
+        }
+        free(pid); free(pf); free(pdu); free(pdv);
+    }
+    if (!rc && n > 2000000000ULL) { set_error("too many particles for one rank"); rc = SPHB_E_ARG; }
+    if (!rc) rc = sphb_mg_upload(c, f, ids, 0, (int)n, b, (int)nb);
+    if (!rc && has_accel) rc = sphb_mg_upload_accel(c, du, dv);
+    if (!rc) c->steps = steps;
+    free(f); free(ids); free(du); free(dv); free(b);
+    return rc;
+}
+
 int sphb_mg_rebalance(sphb_ctx *c, int min_width, double column_cost, double min_imbalance, int *changed_out)
 {
     SPHB_ENTER(c);

@@ -205,6 +205,47 @@ def test_cross_process_peer_store_transport_on_one_device(lib_built, world):
     assert "mg_ipc1dev_check ok" in r.stdout
 
 
+def test_state_parts_continue_on_another_rank_count_and_in_the_oracle(lib_built, oracle_built, tmp_path):
+    """sphb_mg_save_state / sphb_mg_load_state: a dam break saved by 3 slabs after 60 steps continues on 2 slabs
+    with other cuts, on one slab over all columns, and — read by oracle/pyoracle.load_state — in the oracle: each
+    of them ends bit-identical to the uninterrupted single-GPU run of 120 steps."""
+    pkg = lib_built
+    R, g = 0.01, (30.0, -9.81)
+    prm = pkg.default_params(R)
+    box = (2 * R, 1.5, 2 * R, 0.6)
+    fluid, boundary = pkg.scene_block(prm, *box), pkg.scene_boundary(prm)
+    rf, rdu, rdv, rst = single_gpu(pkg, prm, fluid, boundary, 120, g)
+    hist = pkg.column_histogram(prm, fluid)
+    with pkg.SlabGroup(prm, pkg.plan_cuts(hist, 3)) as grp:
+        grp.upload(fluid, boundary); grp.init_boundary(); grp.compute_accel(*g); grp.step(60, *g)
+        parts = grp.save_state(tmp_path / "dam")
+        mid, _, _, _ = grp.download()
+    _, cols = pkg.grid_columns(prm)
+    for cuts in (pkg.plan_cuts(pkg.column_histogram(prm, mid), 2), np.asarray([0, cols], np.int32)):
+        with pkg.SlabGroup(prm, cuts) as grp:
+            grp.load_parts(parts)
+            assert grp.n_fluid == len(fluid)
+            grp.init_boundary()
+            grp.step(60, *g)
+            f, du, dv, _ = grp.download()
+            st = grp.stats()
+        assert_identical(f, du, dv, rf, rdu, rdv)
+        assert st["steps"] == 120 and st["n_lost"] == 0 and st["n_overflow"] == 0
+    # the oracle reads the same parts and continues
+    sv = oracle_built.load_state(parts)
+    assert sv["steps"] == 60 and len(sv["fluid"]) == len(fluid) and np.float32(sv["R"]) == np.float32(R)
+    o = oracle_built.Oracle(R=R, variant="chain")
+    of, ob, odu, odv = sv["fluid"].copy(), sv["boundary"].copy(), sv["du"].copy(), sv["dv"].copy()
+    gb = o.init_boundary(ob)
+    gf = o.grid(len(of))
+    o.step(of, ob, gf, gb, odu, odv, 60, *g)
+    assert_identical(of, odu, odv, rf, rdu, rdv)
+    # a part of another scene is refused
+    with pytest.raises(pkg.SphbError):
+        with pkg.SlabGroup(pkg.default_params(0.02), np.asarray([0, 77], np.int32)) as grp:
+            grp.load_parts(parts)
+
+
 def test_cross_process_recut_on_one_device(lib_built):
     """sphb_mg_rebalance_host across three processes (device 0, peer-store halo transport, bytes of the re-cut
     carried by gloo): a dam break under a strong sideways pull is re-cut every 40 steps — bit-identical to the
