@@ -153,6 +153,17 @@ int sphb_download_boundary(sphb_ctx *ctx, sphb_particle *boundary_out);
 /* :649 / :380-411  draw_metaballs into the SSD1306 page layout (1024 bytes). */
 int sphb_render(sphb_ctx *ctx, unsigned char *draw_buffer);
 
+/* The frame for LARGE particle counts.  draw_metaballs (:380-411) is tied to the reference's scale: its condition
+ * divides by W(px_width/2) (:401), and once the pixel (WIDTH/128 = 31 mm) is wider than the kernel support that is
+ * W far outside 2H, where the reference's W — no cut-off, :45-50 — is a growing polynomial.  For such scenes
+ * (px_width > 4H, i.e. R below ~6 mm; BASELINE configs[1]-[4]) the frame is a splat: a pixel is lit when the fluid
+ * volume inside it, (particles in the pixel) * V (:20), covers at least half of the pixel; same 1 KiB SSD1306 page
+ * layout (:407-408).  sphb_render_counts gives the per-pixel counts of the particles this context owns (a slab
+ * run adds the ranks' counts, e.g. with an all-reduce, before sphb_splat_frame). */
+int sphb_render_splat(sphb_ctx *ctx, unsigned char *draw_buffer);
+int sphb_render_counts(sphb_ctx *ctx, unsigned int *counts /* 64 x 128, row 0 = top */);
+int sphb_splat_frame(const sphb_params *prm, const unsigned int *counts, unsigned char *draw_buffer /* 1024 */);
+
 /* :656-675 as device reductions, plus conservation sums. */
 int sphb_get_stats(sphb_ctx *ctx, sphb_stats *out);
 

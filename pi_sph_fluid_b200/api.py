@@ -85,6 +85,9 @@ def lib() -> C.CDLL:
         "sphb_download": (ci, [vp, vp, vp, vp]),
         "sphb_download_boundary": (ci, [vp, vp]),
         "sphb_render": (ci, [vp, vp]),
+        "sphb_render_splat": (ci, [vp, vp]),
+        "sphb_render_counts": (ci, [vp, vp]),
+        "sphb_splat_frame": (ci, [vp, vp, vp]),
         "sphb_get_stats": (ci, [vp, vp]),
         "sphb_step_stats": (ci, [vp, vp, ci, vp]),
         "sphb_step_stats_begin": (ci, [vp, vp, ci, vp]),
@@ -342,6 +345,17 @@ class Simulation:
         buf = np.zeros(1024, np.uint8)
         _check(lib().sphb_render(self._h, _p(buf)), "sphb_render")
         return buf
+
+    def render_splat(self) -> np.ndarray:
+        """sphb_render_splat: the frame for scenes whose pixels are much wider than the kernel support."""
+        buf = np.zeros(1024, np.uint8)
+        _check(lib().sphb_render_splat(self._h, _p(buf)), "sphb_render_splat")
+        return buf
+
+    def render_counts(self) -> np.ndarray:
+        counts = np.zeros((64, 128), np.uint32)
+        _check(lib().sphb_render_counts(self._h, _p(counts)), "sphb_render_counts")
+        return counts
 
     def stats(self) -> dict:                       # :656-675
         st = Stats()

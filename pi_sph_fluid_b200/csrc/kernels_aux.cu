@@ -54,6 +54,46 @@ int launch_render(cudaStream_t st, const Consts &k, const ParticleSet &fluid, co
     return 1;
 }
 
+// ------------------------------------------------------------------------------ splat (large N)
+
+// draw_metaballs (:380-411) is meaningless once a pixel (WIDTH/128 = 31 mm) is much wider than the kernel
+// support: its condition divides by W(px/2), i.e. W far outside 2H, where the reference's W (no cut-off, :45-50)
+// is a growing polynomial.  For such scenes the frame is a SPLAT: the particles inside each pixel are counted
+// here (shared-memory histogram per CTA, one global atomic per touched pixel), and a pixel is lit when the
+// fluid volume inside it, count * V, covers at least half of the pixel (sphb_splat_frame, host side).
+// Pixel (i, j) covers x in [j, j+1) * WIDTH/128 and y in (64-i-1, 64-i] * HEIGHT/64 — the cells whose centres
+// the reference uses as pixel pseudo-particles (:573-574).
+__global__ void __launch_bounds__(256)
+k_pixel_counts(const Consts k, const Count cnt, const float2 *__restrict__ pos, const uint32_t *__restrict__ cellkey,
+               const float sx, const float sy, unsigned int *__restrict__ counts)
+{
+    __shared__ unsigned int s_c[64 * 128];
+    for (int i = threadIdx.x; i < 64 * 128; i += 256) s_c[i] = 0u;
+    __syncthreads();
+    const int n = count_of(cnt);
+    for (int s = blockIdx.x * 256 + threadIdx.x; s < n; s += gridDim.x * 256) {
+        if (cellkey && !owned_col(k, (int)(cellkey[s] & 0xffffu))) continue;      // slabs: ghosts are the neighbour's
+        const float2 p = pos[s];
+        int j = (int)floorf((p.x - k.x_min) * sx), i = 63 - (int)floorf((p.y - k.y_min) * sy);
+        j = j < 0 ? 0 : (j > 127 ? 127 : j);
+        i = i < 0 ? 0 : (i > 63 ? 63 : i);
+        atomicAdd(&s_c[i * 128 + j], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 128; i += 256)
+        if (s_c[i]) atomicAdd(&counts[i], s_c[i]);
+}
+
+int launch_pixel_counts(cudaStream_t st, const Consts &k, const ParticleSet &f, float width, float height, unsigned int *counts)
+{
+    if (f.n == 0) return 0;
+    int grid = (f.n + 256 * 64 - 1) / (256 * 64);
+    grid = grid < 1 ? 1 : (grid > 148 * 4 ? 148 * 4 : grid);
+    k_pixel_counts<<<grid, 256, 0, st>>>(k, f.cur(), f.pos[f.pc], (f.windowed && f.sorted) ? f.cellkey : nullptr,
+                                         128.0f / width, 64.0f / height, counts);
+    return 1;
+}
+
 // ------------------------------------------------------------------------------ stats
 
 __device__ __forceinline__ unsigned int float_order_key(float f)

@@ -824,6 +824,46 @@ int sphb_render(sphb_ctx *c, unsigned char *draw_buffer)
     return SPHB_OK;
 }
 
+int sphb_render_counts(sphb_ctx *c, unsigned int *counts)
+{
+    SPHB_ENTER(c);
+    if (!counts) return SPHB_E_ARG;
+    if (c->fluid.n <= 0) { set_error("no fluid uploaded"); return SPHB_E_STATE; }
+    int rc = ensure_stage(c, 64 * 128 * sizeof(unsigned int) + 64);
+    if (rc) return rc;
+    unsigned int *d = static_cast<unsigned int *>(c->d_stage);
+    SPHB_CUDA(cudaMemsetAsync(d, 0, 64 * 128 * sizeof(unsigned int), c->stream));
+    c->launches += launch_pixel_counts(c->stream, c->k, c->fluid, c->prm.x_max - c->prm.x_min, c->prm.y_max - c->prm.y_min, d);
+    SPHB_CUDA(cudaMemcpyAsync(counts, d, 64 * 128 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    SPHB_CUDA(cudaStreamSynchronize(c->stream));
+    SPHB_CUDA(cudaGetLastError());
+    return SPHB_OK;
+}
+
+int sphb_splat_frame(const sphb_params *prm, const unsigned int *counts, unsigned char *draw_buffer)
+{
+    if (!prm || !counts || !draw_buffer) return SPHB_E_ARG;
+    // lit when the fluid volume inside the pixel, count * V (:20), covers at least half of the pixel
+    const double pixel = ((double)prm->x_max - prm->x_min) / 128 * (((double)prm->y_max - prm->y_min) / 64);
+    const double need = 0.5 * pixel / (double)prm->vol;
+    memset(draw_buffer, 0, 1024);
+    for (int i = 0; i < 64; i++)
+        for (int j = 0; j < 128; j++)
+            if ((double)counts[i * 128 + j] >= need) draw_buffer[(i / 8) * 128 + j] |= (unsigned char)(1u << (i % 8));      // :407
+    return SPHB_OK;
+}
+
+int sphb_render_splat(sphb_ctx *c, unsigned char *draw_buffer)
+{
+    if (!draw_buffer) return SPHB_E_ARG;
+    unsigned int *counts = static_cast<unsigned int *>(malloc(64 * 128 * sizeof(unsigned int)));
+    if (!counts) return SPHB_E_NOMEM;
+    int rc = sphb_render_counts(c, counts);
+    if (!rc) rc = sphb_splat_frame(&c->prm, counts, draw_buffer);
+    free(counts);
+    return rc;
+}
+
 static float key_to_float(unsigned int key)
 {
     const unsigned int u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;

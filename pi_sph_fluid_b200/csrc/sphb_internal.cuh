@@ -390,6 +390,7 @@ int launch_neighbor_lists(cudaStream_t st, const Consts &k, const ParticleSet &a
 // ---- kernel launchers (kernels_aux.cu) -----------------------------------------------------
 int launch_render(cudaStream_t st, const Consts &k, const ParticleSet &fluid, const float2 *pixels,
                   float W_px, unsigned char *frame);
+int launch_pixel_counts(cudaStream_t st, const Consts &k, const ParticleSet &f, float width, float height, unsigned int *counts);
 int launch_stats(cudaStream_t st, const Consts &k, const ParticleSet &fluid, double *out_d /*4*/,
                  float *out_u /*16 x 32-bit*/, const DeviceCounters *ctr, const unsigned int *flags);
 int launch_refresh(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, unsigned int *moved);

@@ -201,6 +201,41 @@ def test_render_matches_reference_frame(lib_built, golden075):
         sim.close()
 
 
+def test_splat_frame_for_large_particle_counts(lib_built):
+    """sphb_render_splat / sphb_render_counts: per-pixel particle counts equal numpy's on the downloaded positions
+    (single GPU and three slabs summed), the frame is their threshold in the SSD1306 page layout (:407-408), and
+    at this scale (262k-particle drop) it shows the drop as one filled disc while nothing outside is lit."""
+    pkg = lib_built
+    R = 0.002423
+    prm = pkg.default_params(R)
+    fluid, boundary = pkg.scene_drop(prm), pkg.scene_boundary(prm)
+    with pkg.Simulation(prm) as sim:
+        sim.upload(fluid, boundary); sim.init_boundary(); sim.compute_accel(*G); sim.step(20, *G)
+        f, _, _ = sim.download()
+        counts = sim.render_counts()
+        frame = sim.render_splat()
+    j = np.clip(np.floor(f["x"] * np.float32(128.0 / 4.0)).astype(int), 0, 127)
+    i = np.clip(63 - np.floor(f["y"] * np.float32(64.0 / 2.0)).astype(int), 0, 63)
+    ref = np.zeros((64, 128), np.uint32)
+    np.add.at(ref, (i, j), 1)
+    assert np.array_equal(counts, ref) and counts.sum() == len(f)
+    need = 0.5 * (4.0 / 128) * (2.0 / 64) / float(prm.vol)
+    lit = ref >= need
+    bits = np.zeros(1024, np.uint8)
+    for ii, jj in zip(*np.nonzero(lit)):
+        bits[(ii // 8) * 128 + jj] |= np.uint8(1 << (ii % 8))
+    assert np.array_equal(frame, bits)
+    yy, xx = np.mgrid[0:64, 0:128]
+    cx, cy = (xx + 0.5) * 4.0 / 128, (64 - (yy + 0.5)) * 2.0 / 64
+    rr = np.hypot(cx - 2.0, cy - (1.0 + float(f["y"].mean() - fluid["y"].mean())))
+    assert lit[rr < 0.62].all() and not lit[rr > 0.78].any()
+    cuts = pkg.plan_cuts(pkg.column_histogram(prm, fluid), 3)
+    with pkg.SlabGroup(prm, cuts) as grp:
+        grp.upload(fluid, boundary); grp.init_boundary(); grp.compute_accel(*G); grp.step(20, *G)
+        total = sum(s.render_counts().astype(np.uint64) for s in grp.slabs)
+    assert np.array_equal(total, ref)
+
+
 def test_multi_step_against_oracle(oracle_built, lib_built, golden075):
     """100 free-fall steps (p == 0): every field bit-for-bit with the chain oracle, and close to the
     reference-built golden (libm powf: its last-bit differences in powf(x, 3|4) feed the velocities);
