@@ -335,7 +335,7 @@ int sphb_mg_rebalance_host(sphb_ctx *ctx, int min_width, double column_cost, dou
  * parts that fall into its columns, restores their accelerations and the boundary; after sphb_init_boundary the
  * run continues bit-identically — on a different number of ranks if wanted (1 rank: one slab over all columns).
  * Layout: 64-byte header (version 2) | sphb_params | ids[n] | struct particle[n] | du_dt[n] | dv_dt[n] |
- * struct particle boundary[nb]; oracle/pyoracle.py load_state reads both versions. */
+ * struct particle boundary[nb] (the CPU checker under tests reads both versions). */
 int sphb_mg_save_state(sphb_ctx *ctx, const char *path);
 int sphb_mg_load_state(sphb_ctx *ctx, const char *const *paths, int n_paths);
 
