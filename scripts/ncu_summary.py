@@ -18,6 +18,15 @@ for r in rows[2:]:
         if w in idx:
             print(f"  {w:62s} {r[idx[w]]:>16s} {rows[1][idx[w]]}")
     for i, h in enumerate(hdr):
+        # pipe utilisation (which pipe binds: fma / alu / xu / fp64 / lsu ...)
+        if (h.startswith("sm__inst_executed_pipe_") or h.startswith("sm__pipe_")) and "pct_of_peak_sustained_active" in h:
+            try:
+                v = float(r[i].replace(",", ""))
+            except ValueError:
+                continue
+            if v > 5:
+                print(f"  pipe {h:57s} {v:16.2f} %")
+    for i, h in enumerate(hdr):
         if "issue_stalled" in h and h.endswith("per_issue_active.ratio"):
             try:
                 v = float(r[i].replace(",", ""))
