@@ -7,10 +7,13 @@
 //                  ; rank = atomicAdd(count[cell])                       HBM-bound, 44 B/particle
 //   k_scan         exclusive prefix sum of count[] -> start[] (single pass, decoupled
 //                  look-back, warp-shuffle scans), re-zeroing count[]    HBM-bound, 8 B/cell
-//   k_scatter_ids  (deterministic mode) ids into their cell's range in arrival order
+//   k_scatter_ids  (deterministic mode) ids into their cell's range in arrival order — only for
+//                  cells whose population changed in this build (cell_touch)
 //   k_reorder      dst = start[cell] + rank, rank = #ids in the cell below mine
 //                  (deterministic: the reference's ascending-index list order, :110-123)
 //                  or the atomic's arrival rank; moves pos/vel/id        HBM-bound, 40-56 B/particle
+//                  A cell nobody left or entered keeps its particles in their previous (ascending-id)
+//                  order: rank = slot - cell_start_prev[cell], no id lookups.
 #include "sphb_internal.cuh"
 
 namespace sphb {
@@ -50,7 +53,8 @@ __global__ void __launch_bounds__(kStreamThreads)
 k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *__restrict__ vel,
              const float2 *__restrict__ acc, const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellkey,
              uint32_t *__restrict__ key, uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count,
-             DeviceCounters *__restrict__ ctr, const SlabIO io, const StepStats deliver)
+             DeviceCounters *__restrict__ ctr, const SlabIO io, const StepStats deliver,
+             unsigned char *__restrict__ touch, const unsigned char epoch)
 {
     pdl_trigger();
     pdl_wait();
@@ -68,6 +72,12 @@ k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *
     if (live) {
         p = pos[s];
         if (ADVECT || SLAB) v = vel[s];
+        // the cell this slot was sorted into by the previous build: the same function of the same position
+        int row_old = 0, col_old = 0;
+        if (ADVECT && touch != nullptr) {
+            bool c0, o0;
+            cell_of_window(k, p.x, p.y, row_old, col_old, c0, o0);
+        }
         if (ADVECT) {
             const float2 a = acc[s];
             v.x = kick(k, v.x, a.x);          // :616
@@ -85,6 +95,12 @@ k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *
             const uint32_t c = (uint32_t)(row * k.cols + col);   // :113
             key[s] = c;
             rank[s] = atomicAdd(&cell_count[c], 1u);
+        }
+        // a particle that changed cell (or left the window) marks both cells: their populations differ
+        // from the previous build's, so the reorder ranks their particles by id again
+        if (ADVECT && touch != nullptr && (outside || row != row_old || col != col_old)) {
+            touch[row_old * k.cols + col_old] = epoch;
+            if (!outside) touch[row * k.cols + col] = epoch;
         }
     }
     if (SLAB) {
@@ -104,9 +120,17 @@ int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool ad
     if (ps.n == 0) return deliver ? launch_stats_deliver(st, dl) : 0;
     const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
     const uint32_t *keys = ps.sorted ? ps.cellkey : nullptr;
+    // a new build starts: its epoch for the cell marks, and whether the marks will be complete (the input
+    // is the previous sorted order, advanced in place)
+    ps.touch_ok = SPHB_TOUCH && ps.sorted && ps.cell_touch != nullptr;
+    if (++ps.touch_epoch > 255u) {
+        ps.touch_epoch = 1u;
+        if (ps.cell_touch) cudaMemsetAsync(ps.cell_touch, 0, (size_t)k.ncells, st);
+    }
+    unsigned char *touch = ps.touch_ok ? ps.cell_touch : nullptr;
 #define SPHB_ADV(A, S, IO)                                                                                  \
     launch_pdl(st, grid, kStreamThreads, k_advect_bin<A, S>, k, ps.cur(), ps.pos[ps.pc], ps.vel[ps.vc], ps.acc, \
-               ps.id[ps.ic], keys, ps.key, ps.rank, ps.cell_count, ctr, IO, dl)
+               ps.id[ps.ic], keys, ps.key, ps.rank, ps.cell_count, ctr, IO, dl, touch, (unsigned char)ps.touch_epoch)
     if (slab) { if (advect) SPHB_ADV(true, true, *slab); else SPHB_ADV(false, true, *slab); }
     else { if (advect) SPHB_ADV(true, false, SlabIO()); else SPHB_ADV(false, false, SlabIO()); }
 #undef SPHB_ADV
@@ -166,7 +190,7 @@ __global__ void __launch_bounds__(kStreamThreads)
 k_bin_recv(const Consts k, const SlabIO io, const int *__restrict__ n_cur, int *__restrict__ n_in,
            float2 *__restrict__ pos, float2 *__restrict__ vel, uint32_t *__restrict__ id,
            uint32_t *__restrict__ key, uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count,
-           DeviceCounters *__restrict__ ctr)
+           DeviceCounters *__restrict__ ctr, unsigned char *__restrict__ touch, const unsigned char epoch)
 {
     __shared__ uint32_t s_cnt[2];
     pdl_trigger();
@@ -233,6 +257,7 @@ k_bin_recv(const Consts k, const SlabIO io, const int *__restrict__ n_cur, int *
     const uint32_t c = (uint32_t)(row * k.cols + col);
     key[slot] = c;
     rank[slot] = atomicAdd(&cell_count[c], 1u);
+    if (touch != nullptr) touch[c] = epoch;      // an arrival (ghost or migrant): the cell is ranked by id again
 }
 
 int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const SlabIO &slab, DeviceCounters *ctr)
@@ -240,7 +265,8 @@ int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const Sla
     const int threads = 2 * slab.recv[0].cap > 0 ? 2 * slab.recv[0].cap : 1;
     const int grid = (threads + kStreamThreads - 1) / kStreamThreads;
     launch_pdl(st, grid, kStreamThreads, k_bin_recv, k, slab, ps.d_n_cur, ps.d_n_in, ps.pos[ps.pc], ps.vel[ps.vc],
-               ps.id[ps.ic], ps.key, ps.rank, ps.cell_count, ctr);
+               ps.id[ps.ic], ps.key, ps.rank, ps.cell_count, ctr, ps.touch_ok ? ps.cell_touch : nullptr,
+               (unsigned char)ps.touch_epoch);
     return 1;
 }
 
@@ -380,6 +406,8 @@ k_scan(uint32_t *__restrict__ count, uint32_t *__restrict__ start, const int n,
 int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc, DeviceCounters *ctr)
 {
     const int n_tiles = (k.ncells + kScanTile - 1) / kScanTile;
+    // the previous build's cell_start stays readable for the reorder (ParticleSet::cell_start_prev)
+    if (ps.cell_start_prev) { uint32_t *t = ps.cell_start; ps.cell_start = ps.cell_start_prev; ps.cell_start_prev = t; }
     sc.epoch = (sc.epoch + 1) & 0x3fffffffu;
     if (sc.epoch == 0) sc.epoch = 1;   // 0 is the memset state ("never written")
     const unsigned long long base = sc.launches;   // tiles handed out so far
@@ -394,7 +422,7 @@ int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc
 __global__ void __launch_bounds__(kStreamThreads)
 k_scatter_ids(const Count cnt, const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
               const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ start,
-              uint32_t *__restrict__ ids_tmp)
+              uint32_t *__restrict__ ids_tmp, const unsigned char *__restrict__ touch, const unsigned char epoch)
 {
     pdl_trigger();
     pdl_wait();
@@ -402,6 +430,7 @@ k_scatter_ids(const Count cnt, const uint32_t *__restrict__ key, const uint32_t 
     if (s >= count_of(cnt)) return;
     const uint32_t c = key[s];
     if (c == kTrashKey) return;
+    if (touch != nullptr && touch[c] != epoch) return;      // the cell keeps its previous order (k_reorder)
     ids_tmp[start[c] + rank[s]] = id_in[s];
 }
 
@@ -413,7 +442,8 @@ k_reorder(const Count cnt, const uint32_t *__restrict__ key, const uint32_t *__r
           const uint32_t *__restrict__ id_in, const float *__restrict__ mass_in,
           const float *__restrict__ aux_in, float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
           uint32_t *__restrict__ id_out, float *__restrict__ mass_out, float *__restrict__ aux_out,
-          uint32_t *__restrict__ cellkey_out, const int cols)
+          uint32_t *__restrict__ cellkey_out, const int cols, const uint32_t *__restrict__ start_prev,
+          const unsigned char *__restrict__ touch, const unsigned char epoch)
 {
     pdl_trigger();
     pdl_wait();
@@ -424,7 +454,11 @@ k_reorder(const Count cnt, const uint32_t *__restrict__ key, const uint32_t *__r
     const uint32_t my = id_in[s];
     const uint32_t b = start[c];
     uint32_t dst;
-    if (DET) {
+    if (DET && touch != nullptr && touch[c] != epoch) {
+        // nobody left or entered this cell since the previous build: its particles are the slots
+        // [start_prev[c], start_prev[c+1]) of the input, already in ascending-id order
+        dst = b + ((uint32_t)s - start_prev[c]);
+    } else if (DET) {
         // rank = number of ids in my cell smaller than mine -> ascending original index,
         // the order the reference's tail-append produces (:110-123)
         const uint32_t e = start[c + 1];
@@ -448,8 +482,11 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
     const int grid = (ps.n + kStreamThreads - 1) / kStreamThreads;
     const Count in = ps.d_n_in ? ps.in() : ps.cur();
     int launches = 0;
+    const unsigned char *touch = (deterministic && ps.touch_ok) ? ps.cell_touch : nullptr;
+    const unsigned char epoch = (unsigned char)ps.touch_epoch;
     if (deterministic) {
-        launch_pdl(st, grid, kStreamThreads, k_scatter_ids, in, ps.key, ps.rank, ps.id[ps.ic], ps.cell_start, ps.ids_tmp);
+        launch_pdl(st, grid, kStreamThreads, k_scatter_ids, in, ps.key, ps.rank, ps.id[ps.ic], ps.cell_start, ps.ids_tmp,
+                   touch, epoch);
         launches++;
     }
     const bool has_mass = ps.mass[0] != nullptr;
@@ -461,7 +498,7 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
 #define SPHB_REORDER(D, M, A)                                                                           \
     launch_pdl(st, grid, kStreamThreads, k_reorder<D, M, A>, in, ps.key, ps.rank, ps.cell_start, ps.ids_tmp, \
         ps.pos[ps.pc], ps.vel[ps.vc], ps.id[ps.ic], mass_in, aux_in, ps.pos[ps.pc ^ 1],                  \
-        ps.vel[ps.vc ^ 1], ps.id[ps.ic ^ 1], mass_out, aux_out, ps.cellkey, k.cols)
+        ps.vel[ps.vc ^ 1], ps.id[ps.ic ^ 1], mass_out, aux_out, ps.cellkey, k.cols, ps.cell_start_prev, touch, epoch)
     if (deterministic) {
         if (has_mass && has_aux) SPHB_REORDER(true, true, true);
         else if (has_mass) SPHB_REORDER(true, true, false);

@@ -39,6 +39,7 @@ static void free_set(ParticleSet &ps)
     }
     cudaFree(ps.acc); cudaFree(ps.rho_prr); cudaFree(ps.p); cudaFree(ps.key); cudaFree(ps.rank);
     cudaFree(ps.ids_tmp); cudaFree(ps.cell_count); cudaFree(ps.cell_start); cudaFree(ps.cellkey);
+    cudaFree(ps.cell_start_prev); cudaFree(ps.cell_touch);
     cudaFree(ps.nbr_list); cudaFree(ps.nbr_count); cudaFree(ps.chunk_rec); cudaFree(ps.chunk_queue);
     ps = ParticleSet();
 }
@@ -89,6 +90,10 @@ int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_ma
     SPHB_CUDA(dmalloc(&ps.cell_start, (size_t)ncells + 8));
     SPHB_CUDA(cudaMemset(ps.cell_count, 0, ((size_t)ncells + 8) * sizeof(uint32_t)));
     SPHB_CUDA(cudaMemset(ps.cell_start, 0, ((size_t)ncells + 8) * sizeof(uint32_t)));
+    SPHB_CUDA(dmalloc(&ps.cell_start_prev, (size_t)ncells + 8));
+    SPHB_CUDA(dmalloc(&ps.cell_touch, (size_t)ncells + 8));
+    SPHB_CUDA(cudaMemset(ps.cell_start_prev, 0, ((size_t)ncells + 8) * sizeof(uint32_t)));
+    SPHB_CUDA(cudaMemset(ps.cell_touch, 0, (size_t)ncells + 8));
     // the memsets above ran on the legacy default stream, which does not order against the
     // handle's non-blocking stream
     SPHB_CUDA(cudaDeviceSynchronize());

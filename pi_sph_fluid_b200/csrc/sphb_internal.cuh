@@ -135,6 +135,14 @@ struct ParticleSet {
     uint32_t *ids_tmp = nullptr;              // deterministic-rank scratch
     uint32_t *cell_count = nullptr;           // ncells, zero between builds
     uint32_t *cell_start = nullptr;           // ncells + 1
+    // Deterministic reorder without the id pass (kernels_build.cu): the scan writes into the other of two
+    // cell_start buffers, so the reorder still sees where every cell began in the PREVIOUS sorted order, and
+    // the binning kernels mark (with the build's epoch) every cell a particle left or entered.  A cell that
+    // is not marked holds exactly the particles it held before, in the same ascending-id order.
+    uint32_t *cell_start_prev = nullptr;      // ncells + 1: cell_start of the previous build
+    unsigned char *cell_touch = nullptr;      // ncells: epoch of the last build that changed the cell's population
+    unsigned int touch_epoch = 0;             // 1..255 (0 = never; the array is cleared when the epoch wraps)
+    bool touch_ok = false;                    // this build's input is the previous sorted order: marks are complete
     bool sorted = false;
     bool counters_dirty = false;              // a grid build ran since the density pass last published the build counters
     bool uniform_mass = true;
@@ -357,6 +365,9 @@ int launch_stats_deliver(cudaStream_t st, const StepStats &ss);
 int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const SlabIO &slab, DeviceCounters *ctr);
 int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc, DeviceCounters *ctr);
 int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deterministic);
+#ifndef SPHB_TOUCH
+#define SPHB_TOUCH 1      // 0: every particle goes through the id pass of the deterministic reorder (round-1 behaviour)
+#endif
 int launch_aos_to_soa(cudaStream_t st, const sphb_particle *aos, ParticleSet &ps, bool is_boundary, int n = -1,
                       const uint32_t *ids = nullptr, uint32_t id_base = 0, uint32_t m0_bits = 0,
                       unsigned int *mass_differs = nullptr);
