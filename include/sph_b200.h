@@ -210,6 +210,12 @@ int sphb_handover_lists(sphb_ctx *ctx, int cap, int *counts, int *lists, unsigne
  * whether the host verified the shortcuts for this context's H (variants 0, 2 are only then exact). */
 int sphb_probe_force_pair(sphb_ctx *ctx, int n, const float *pairs, int variant, float *out_txy, int *exact_shortcuts);
 
+/* Grid builds of the fluid set, so far, whose deterministic reorder took the in-cell order of unchanged cells
+ * from the previous build (cell marks) instead of ranking every particle by id.  Sets below
+ * 2^20 slots do not use the marks unless SPHB_TOUCH_MIN_SLOTS is set in the environment when the set is
+ * uploaded (the parity tests run small scenes with SPHB_TOUCH_MIN_SLOTS=0). */
+int sphb_reorder_marks(sphb_ctx *ctx, unsigned long long *builds_with_marks);
+
 /* ---- measurement hooks --------------------------------------------------------------- */
 
 enum { SPHB_K_ADVECT_BIN = 0, SPHB_K_SCAN, SPHB_K_REORDER, SPHB_K_DENSITY, SPHB_K_FORCE,

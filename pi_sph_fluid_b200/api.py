@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         "sphb_probe_force_pair": (ci, [vp, ci, vp, ci, vp, vp]),
         "sphb_handover_lists": (ci, [vp, ci, vp, vp, vp]),
         "sphb_flush_l2": (ci, [vp]),
+        "sphb_reorder_marks": (ci, [vp, vp]),
         "sphb_stream": (vp, [vp]),
         "sphb_launch_count": (C.c_ulonglong, [vp]),
         "sphb_last_error": (C.c_char_p, []),
@@ -408,6 +409,12 @@ class Simulation:
         ln = (C.c_ulonglong * len(KERNEL_NAMES))()
         _check(lib().sphb_profile_read(self._h, ms, ln, int(reset)), "sphb_profile_read")
         return {k: {"ms": ms[i], "launches": int(ln[i])} for i, k in enumerate(KERNEL_NAMES)}
+
+    def reorder_marks(self) -> int:
+        """grid builds whose deterministic reorder used the cell marks (sphb_reorder_marks)"""
+        n = C.c_ulonglong(0)
+        _check(lib().sphb_reorder_marks(self._h, C.byref(n)), "sphb_reorder_marks")
+        return int(n.value)
 
     def flush_l2(self):
         _check(lib().sphb_flush_l2(self._h), "sphb_flush_l2")

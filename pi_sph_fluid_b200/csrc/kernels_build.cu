@@ -15,10 +15,22 @@
 //                  A cell nobody left or entered keeps its particles in their previous (ascending-id)
 //                  order: rank = slot - cell_start_prev[cell], no id lookups.
 #include "sphb_internal.cuh"
+#include <cstdlib>
 
 namespace sphb {
 
 // ------------------------------------------------------------------------ advect + bin
+
+#ifndef SPHB_TOUCH_MIN_SLOTS
+#define SPHB_TOUCH_MIN_SLOTS (1 << 20)
+#endif
+// smallest set (in slots) whose deterministic reorder uses the cell marks; SPHB_TOUCH_MIN_SLOTS in the
+// environment overrides it when a set is allocated (the parity tests run small scenes with 0)
+int touch_min_slots()
+{
+    const char *e = getenv("SPHB_TOUCH_MIN_SLOTS");
+    return (e && *e) ? atoi(e) : SPHB_TOUCH_MIN_SLOTS;
+}
 
 // Appends (p, v, id) of the lanes with `want` to a halo message: one atomic per warp, the lanes
 // take consecutive entries.  Every lane of the warp must call this.
@@ -72,6 +84,8 @@ k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *
     if (live) {
         p = pos[s];
         if (ADVECT || SLAB) v = vel[s];
+        float2 a = make_float2(0.0f, 0.0f);
+        if (ADVECT) a = acc[s];            // all three loads in flight before anything waits for one of them
         // the cell this slot was sorted into by the previous build: the same function of the same position
         int row_old = 0, col_old = 0;
         if (ADVECT && touch != nullptr) {
@@ -79,7 +93,6 @@ k_advect_bin(const Consts k, const Count cnt, float2 *__restrict__ pos, float2 *
             cell_of_window(k, p.x, p.y, row_old, col_old, c0, o0);
         }
         if (ADVECT) {
-            const float2 a = acc[s];
             v.x = kick(k, v.x, a.x);          // :616
             v.y = kick(k, v.y, a.y);          // :617
             p.x = drift(k, p.x, v.x);         // :622
@@ -122,7 +135,9 @@ int launch_advect_bin(cudaStream_t st, const Consts &k, ParticleSet &ps, bool ad
     const uint32_t *keys = ps.sorted ? ps.cellkey : nullptr;
     // a new build starts: its epoch for the cell marks, and whether the marks will be complete (the input
     // is the previous sorted order, advanced in place)
-    ps.touch_ok = SPHB_TOUCH && ps.sorted && ps.cell_touch != nullptr;
+    // (below ~1M slots the build kernels are latency-bound and the marks' extra dependent load costs more
+    // than the id traffic it saves: 65.8 vs 66.7 us/step at 262k particles, 9.88 vs 9.75 ms at 64M)
+    ps.touch_ok = SPHB_TOUCH && ps.sorted && ps.cell_touch != nullptr && ps.n >= ps.touch_min_slots;
     if (++ps.touch_epoch > 255u) {
         ps.touch_epoch = 1u;
         if (ps.cell_touch) cudaMemsetAsync(ps.cell_touch, 0, (size_t)k.ncells, st);
@@ -453,11 +468,15 @@ k_reorder(const Count cnt, const uint32_t *__restrict__ key, const uint32_t *__r
     if (c == kTrashKey) return;      // left this rank's window (slabs) — not carried over
     const uint32_t my = id_in[s];
     const uint32_t b = start[c];
+    // (the three per-cell words are loaded side by side, not one after the other's branch)
+    const bool keep = DET && touch != nullptr;
+    const unsigned char mark = keep ? touch[c] : epoch;
+    const uint32_t b_prev = keep ? start_prev[c] : 0u;
     uint32_t dst;
-    if (DET && touch != nullptr && touch[c] != epoch) {
+    if (mark != epoch) {
         // nobody left or entered this cell since the previous build: its particles are the slots
         // [start_prev[c], start_prev[c+1]) of the input, already in ascending-id order
-        dst = b + ((uint32_t)s - start_prev[c]);
+        dst = b + ((uint32_t)s - b_prev);
     } else if (DET) {
         // rank = number of ids in my cell smaller than mine -> ascending original index,
         // the order the reference's tail-append produces (:110-123)
@@ -484,6 +503,7 @@ int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deter
     int launches = 0;
     const unsigned char *touch = (deterministic && ps.touch_ok) ? ps.cell_touch : nullptr;
     const unsigned char epoch = (unsigned char)ps.touch_epoch;
+    if (touch) ps.touch_builds++;
     if (deterministic) {
         launch_pdl(st, grid, kStreamThreads, k_scatter_ids, in, ps.key, ps.rank, ps.id[ps.ic], ps.cell_start, ps.ids_tmp,
                    touch, epoch);

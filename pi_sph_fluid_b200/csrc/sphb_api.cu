@@ -57,9 +57,11 @@ int alloc_set(ParticleSet &ps, int n, int ncells, bool is_boundary, bool need_ma
     if (ps.cap >= n && ps.cell_count && (need_mass ? ps.mass[0] != nullptr : true) &&
         (is_boundary ? ps.aux[0] != nullptr : ps.acc != nullptr)) {
         ps.n = n;
+        ps.touch_min_slots = touch_min_slots();
         return SPHB_OK;
     }
     free_set(ps);
+    ps.touch_min_slots = touch_min_slots();
     const size_t m = (size_t)n + 4;
     for (int i = 0; i < 2; i++) {
         SPHB_CUDA(dmalloc(&ps.pos[i], m));
@@ -916,6 +918,14 @@ int sphb_get_stats(sphb_ctx *c, sphb_stats *out)
     SPHB_CUDA(cudaStreamSynchronize(c->stream));
     decode_stats(c, h, out);
     if (c->mg.on && (out->n_overflow & (1u << 30))) { c->mg.comm_failed = true; return mg_health(c); }
+    return SPHB_OK;
+}
+
+int sphb_reorder_marks(sphb_ctx *c, unsigned long long *builds_with_marks)
+{
+    SPHB_ENTER(c);
+    if (!builds_with_marks) { set_error("null argument"); return SPHB_E_ARG; }
+    *builds_with_marks = c->fluid.touch_builds;
     return SPHB_OK;
 }
 

@@ -143,6 +143,8 @@ struct ParticleSet {
     unsigned char *cell_touch = nullptr;      // ncells: epoch of the last build that changed the cell's population
     unsigned int touch_epoch = 0;             // 1..255 (0 = never; the array is cleared when the epoch wraps)
     bool touch_ok = false;                    // this build's input is the previous sorted order: marks are complete
+    unsigned long long touch_builds = 0;      // builds that used the marks (sphb_reorder_marks)
+    int touch_min_slots = 1 << 20;            // sets smaller than this keep the id pass for every cell (touch_min_slots())
     bool sorted = false;
     bool counters_dirty = false;              // a grid build ran since the density pass last published the build counters
     bool uniform_mass = true;
@@ -365,6 +367,7 @@ int launch_stats_deliver(cudaStream_t st, const StepStats &ss);
 int launch_bin_recv(cudaStream_t st, const Consts &k, ParticleSet &ps, const SlabIO &slab, DeviceCounters *ctr);
 int launch_scan(cudaStream_t st, const Consts &k, ParticleSet &ps, ScanState &sc, DeviceCounters *ctr);
 int launch_reorder(cudaStream_t st, const Consts &k, ParticleSet &ps, bool deterministic);
+int touch_min_slots();
 #ifndef SPHB_TOUCH
 #define SPHB_TOUCH 1      // 0: every particle goes through the id pass of the deterministic reorder (round-1 behaviour)
 #endif
