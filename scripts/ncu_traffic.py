@@ -5,7 +5,7 @@ roofline.traffic:  ncu_traffic.py workload=file.ncu-rep [workload=file.ncu-rep .
 import csv, io, json, subprocess, sys, collections
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9,
-        "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}     # times in microseconds
+        "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}     # times in microseconds
 SHORT = {"k_density": "density", "k_force": "force", "k_advect_bin": "advect_bin", "k_scan": "scan",
          "k_scatter_ids": "scatter_ids", "k_reorder": "reorder"}
 
