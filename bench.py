@@ -44,7 +44,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "fluid-particle-updates/sec"
 UNIT = "particle-updates/s"
 G = (0.0, -9.81)
-CAP_FACTOR = 1.10        # slabs: particle slots per rank / particles uploaded to it
+CAP_FACTOR = 1.05        # slabs: particle slots per rank / particles uploaded to it
 
 # algorithmic HBM bytes / particle / launch (DESIGN.md "Kernels")
 ALGO_BYTES = {"advect_bin": 44.0, "reorder": 40.0, "density": 16.0, "force": 40.0}
@@ -485,8 +485,12 @@ def run_gpu_slabs(args, spec, rank, world):
     part, base = pkg.scene_block_slab(prm, *box, int(cuts[rank]), int(cuts[rank + 1]))
     boundary = pkg.scene_boundary(prm)
     n = len(part)
-    halo_est = int(hist[max(int(cuts[rank]) - 2, 0):int(cuts[rank]) + 2].sum() + hist[int(cuts[rank + 1]) - 2:int(cuts[rank + 1]) + 2].sum())
-    halo_cap = max(8192, 2 * max(int(h) for h in [halo_est]))
+    # one message carries the sender's two columns next to a cut (ghosts for the receiver) plus the few particles
+    # that crossed it: capacity = 2 x the fuller side of the fullest cut (the same for every rank)
+    def side(c):
+        return max(int(hist[max(c - 2, 0):c].sum()), int(hist[c:c + 2].sum()))
+    halo_est = max(side(int(cuts[rank])) if rank > 0 else 0, side(int(cuts[rank + 1])) if rank < world - 1 else 0)
+    halo_cap = max(8192, 2 * halo_est)
     cap_t = torch.tensor([halo_cap], device=f"cuda:{dev}")
     dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
     halo_cap = int(cap_t.item())
@@ -496,11 +500,13 @@ def run_gpu_slabs(args, spec, rank, world):
     dist.broadcast_object_list(ident, src=0)
 
     def make():
-        # particle slots per rank: 1.10 x its particles + four messages' worth (the library default is
-        # 1.25 x; kernels are launched for the slot capacity, so unused slots cost empty CTAs: 1.00 x
-        # measured 2 % faster than 1.25 x at N = 2).  SPHB_BENCH_CAP_FACTOR overrides (0: library default).
+        # particle slots per rank: 1.05 x its particles + two messages' worth (the least the library takes; its
+        # own default is 1.25 x + four messages, for long runs that do not re-cut).  Kernels are launched for
+        # the slot capacity, so unused slots cost empty CTAs (~1.5 us per 1184 of them): at N = 8 the round-1
+        # sizing (1.10 x + four messages of twice the size) left 1.8M empty slots per rank, ~3 % of the step.
+        # An overflow would show in merged_stats.n_overflow.  SPHB_BENCH_CAP_FACTOR overrides (0: library default).
         capf = float(os.environ.get("SPHB_BENCH_CAP_FACTOR", str(CAP_FACTOR)))
-        pcap = int(capf * n) + 4 * halo_cap if capf > 0 else 0
+        pcap = int(capf * n) + 2 * halo_cap + 1024 if capf > 0 else 0
         s_ = pkg.Slab(prm, rank, world, int(cuts[rank]), int(cuts[rank + 1]), particle_capacity=pcap, halo_capacity=halo_cap)
         return s_
     # transport of the per-step halo + migration message: "ipc" = the advect+bin kernel stores the entries
@@ -600,6 +606,9 @@ def run_gpu_slabs(args, spec, rank, world):
     prof = sim.profile_read(reset=True)
     sim.profile(0)
     st = sim.allreduce_stats()
+    if st["n_lost"] or st["n_overflow"] or st["n_fluid"] != n_total:
+        raise SystemExit(f"slab run lost particles or overflowed its slots (n_fluid {st['n_fluid']} of {n_total}, n_lost {st['n_lost']}, "
+                         f"n_overflow {st['n_overflow']}): the line would not describe the configured workload")
     info = sim.info()
     n_local = sim.stats()["n_fluid"]
     hbm_peak, sm_max_mhz, peak_src = read_peaks()
