@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Long run at full size on one GPU: the 4M-particle dam break (BASELINE configs[2]) for 20,000 leapfrog
-steps, statistics every 2,000 steps -> gpurun_out/long_run_dam4m.json.  Checks that mass is exact, that
-nothing escapes or overflows and that no field goes non-finite while the column collapses."""
-import json, sys, time
+steps, statistics every 2,000 steps -> gpurun_out/long_run_dam4m.json (argv[2] renames it).  Checks that mass is
+exact, that nothing escapes or overflows and that no field goes non-finite while the column collapses; the
+SHA-256 of the final state lets two runs be compared bit for bit (e.g. SPHB_TOUCH_MIN_SLOTS=1073741824 against
+the default: the deterministic reorder with and without the cell marks)."""
+import hashlib, json, os, sys, time
 from pathlib import Path
 import numpy as np
 ROOT = Path(__file__).resolve().parents[1]
@@ -29,10 +31,15 @@ with pkg.Simulation(prm) as sim:
     wall = time.perf_counter() - t0
     f, du, dv = sim.download()
 finite = bool(all(np.isfinite(f[k]).all() for k in ("x", "y", "u", "v", "rho", "p")) and np.isfinite(du).all() and np.isfinite(dv).all())
+h = hashlib.sha256()
+for k in ("x", "y", "u", "v", "rho", "p"):
+    h.update(np.ascontiguousarray(f[k]).tobytes())
+h.update(np.ascontiguousarray(du).tobytes()); h.update(np.ascontiguousarray(dv).tobytes())
 out = {"workload": "dam_break_R0.0005_4M (BASELINE configs[2])", "n_fluid": int(len(fluid)), "steps": steps, "wall_s": round(wall, 2),
+       "state_sha256": h.hexdigest(), "reorder_marks_env": os.environ.get("SPHB_TOUCH_MIN_SLOTS", "default (marks on: >= 2^20 slots)"),
        "updates_per_s_incl_stats": len(fluid) * steps / wall, "all_finite": finite,
        "x_front_max": float(f["x"].max()), "y_max": float(f["y"].max()), "samples": rows}
 Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
-(ROOT / "gpurun_out" / "long_run_dam4m.json").write_text(json.dumps(out, indent=1))
+(ROOT / "gpurun_out" / (sys.argv[2] if len(sys.argv) > 2 else "long_run_dam4m.json")).write_text(json.dumps(out, indent=1))
 assert finite and all(r["mass_rel_err"] < 1e-12 and r["n_escaped"] == 0 for r in rows), "long run failed its checks"
-print("long run ok:", steps, "steps,", round(wall, 1), "s")
+print("long run ok:", steps, "steps,", round(wall, 1), "s, state sha256", h.hexdigest()[:16])
