@@ -460,6 +460,22 @@ def scaling_note():
             "n1": "the whole 64M-particle scene on one B200", "n_gt_1": "x-slabs of it, 64M / N particles per GPU"}
 
 
+def slab_halo_capacity(hist, cuts, rank: int, world: int) -> int:
+    """Entries one halo + migration message of this rank must hold.  A message carries the sender's two columns
+    next to a cut (ghosts for the receiver) plus the few particles that crossed it: 2 x the fuller side of the
+    fuller of this rank's cuts (the ranks then agree on the maximum)."""
+    def side(c):
+        return max(int(hist[max(c - 2, 0):c].sum()), int(hist[c:c + 2].sum()))
+    est = max(side(int(cuts[rank])) if rank > 0 else 0, side(int(cuts[rank + 1])) if rank < world - 1 else 0)
+    return max(8192, 2 * est)
+
+
+def slab_particle_capacity(n: int, halo_cap: int, factor: float) -> int:
+    """Particle slots of a rank that uploads n particles: factor x n + two messages' worth (the least the library
+    takes is n + 2 x halo_cap); 0 = the library's own default (1.25 x + four messages)."""
+    return int(factor * n) + 2 * halo_cap + 1024 if factor > 0 else 0
+
+
 def run_gpu_slabs(args, spec, rank, world):
     """N > 1: the dam-break block cut into x-slabs at the particle-count quantiles, one process per GPU,
     halo + migration as peer stores over NVLink (or NCCL send/recv).  Strong scaling: the same scene at every N."""
@@ -485,12 +501,7 @@ def run_gpu_slabs(args, spec, rank, world):
     part, base = pkg.scene_block_slab(prm, *box, int(cuts[rank]), int(cuts[rank + 1]))
     boundary = pkg.scene_boundary(prm)
     n = len(part)
-    # one message carries the sender's two columns next to a cut (ghosts for the receiver) plus the few particles
-    # that crossed it: capacity = 2 x the fuller side of the fullest cut (the same for every rank)
-    def side(c):
-        return max(int(hist[max(c - 2, 0):c].sum()), int(hist[c:c + 2].sum()))
-    halo_est = max(side(int(cuts[rank])) if rank > 0 else 0, side(int(cuts[rank + 1])) if rank < world - 1 else 0)
-    halo_cap = max(8192, 2 * halo_est)
+    halo_cap = slab_halo_capacity(hist, cuts, rank, world)
     cap_t = torch.tensor([halo_cap], device=f"cuda:{dev}")
     dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
     halo_cap = int(cap_t.item())
@@ -506,7 +517,7 @@ def run_gpu_slabs(args, spec, rank, world):
         # sizing (1.10 x + four messages of twice the size) left 1.8M empty slots per rank, ~3 % of the step.
         # An overflow would show in merged_stats.n_overflow.  SPHB_BENCH_CAP_FACTOR overrides (0: library default).
         capf = float(os.environ.get("SPHB_BENCH_CAP_FACTOR", str(CAP_FACTOR)))
-        pcap = int(capf * n) + 2 * halo_cap + 1024 if capf > 0 else 0
+        pcap = slab_particle_capacity(n, halo_cap, capf)
         s_ = pkg.Slab(prm, rank, world, int(cuts[rank]), int(cuts[rank + 1]), particle_capacity=pcap, halo_capacity=halo_cap)
         return s_
     # transport of the per-step halo + migration message: "ipc" = the advect+bin kernel stores the entries

@@ -37,3 +37,31 @@ def test_bench_slab_arm_releases_what_it_connects():
     slabs = src[src.index("def run_gpu_slabs("):src.index("def main(")]
     assert "release(" not in single and "connect_ipc" not in single
     assert slabs.count("release(s") >= 2 and "disconnect_ipc" in slabs and "connect_ipc" in slabs
+
+
+def test_bench_slab_sizing_covers_the_messages_and_the_library_minimum():
+    """bench.py sizes a slab's message buffers from the column histogram around its cuts and its particle slots
+    from the particles it uploads: every message must fit (two columns of the sender + slack), the slots must
+    meet the library's minimum (n + two messages, sphb_mg_upload), and an end rank has one neighbour only."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(3)
+    hist = np.zeros(400, np.int64)
+    hist[10:250] = rng.integers(9000, 15000, 240)          # a block of fluid, the rest of the tank dry
+    cuts = [0, 70, 130, 190, 400]
+    world = len(cuts) - 1
+    caps = [bench.slab_halo_capacity(hist, cuts, r, world) for r in range(world)]
+    for r in range(world):
+        lo, hi = cuts[r], cuts[r + 1]
+        sends = ([int(hist[lo:lo + 2].sum())] if r > 0 else []) + ([int(hist[hi - 2:hi].sum())] if r < world - 1 else [])
+        recvs = ([int(hist[lo - 2:lo].sum())] if r > 0 else []) + ([int(hist[hi:hi + 2].sum())] if r < world - 1 else [])
+        assert all(2 * m <= caps[r] for m in sends + recvs)
+    cap = max(caps)
+    assert bench.slab_halo_capacity(hist, cuts, 0, 1) == 8192                 # no neighbour: the floor
+    n = int(hist[cuts[1]:cuts[2]].sum())
+    slots = bench.slab_particle_capacity(n, cap, bench.CAP_FACTOR)
+    assert slots >= n + 2 * cap and slots <= 1.06 * n + 2 * cap + 1024
+    assert bench.slab_particle_capacity(n, cap, 0.0) == 0                     # library default
